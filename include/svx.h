@@ -1,0 +1,130 @@
+/*
+ * svx.h -- C-ABI of the B200-native SVision encode-and-classify path (libsvx.so).
+ *
+ * The reference has no plugin/FFI interface: the seam is
+ *   Predict(chrom, segments_out_file).run(out_path_prefix, options)
+ *                                         (reference: src/network/predict.py:15,148)
+ * and inside it exactly two calls are replaced by this library:
+ *   batch_generator.next_batch(batch_size)          src/network/predict.py:207
+ *       -> src/network/create_batch.py:88-155  (-> src/segmentplot/plot_segment.py:33-73)
+ *   sess.run([score, argmax, softmax], feed_dict)   src/network/predict.py:209-210
+ *       -> src/network/alexnet.py:26-58
+ * The ctypes binding a maintainer would add on the reference side is shown in INTEGRATION.md.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no torch / C++ types;
+ *   - every function returns 0 on success or a negative svx_status; the message of the last
+ *     failure on the calling thread is returned by svx_last_error();
+ *   - "rows" are packed candidate sites, int32[n][12]:
+ *        xS1 xE1 yS1 yE1 f1  xS2 xE2 yS2 yE2 f2  len_a len_b
+ *     (the 12 '_'-joined tokens of create_batch.py:45; f = 1 for the token 'True', 0 otherwise;
+ *     xE is carried but ignored, as create_batch.py:106,121 ignore it);
+ *   - `stream` is a cudaStream_t passed as void* (NULL = the legacy default stream);
+ *   - device pointers must belong to the handle's device; the caller owns every buffer it
+ *     passes; the library owns weights and workspaces; nothing is allocated on the hot path
+ *     after svx_create;
+ *   - a handle is not thread-safe and not fork-safe (create it in the process that uses it).
+ */
+#ifndef SVX_H_
+#define SVX_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SVX_IMG 227            /* src/network/predict.py:167, create_batch.py:13 */
+#define SVX_ROW_FIELDS 12
+#define SVX_NUM_CLASSES 5      /* 0 DEL, 1 INS, 2 INV, 3 DUP, 4 tDUP: predict.py:133-142 */
+
+typedef enum {
+    SVX_OK = 0,
+    SVX_ERR_INVALID = -1,      /* bad argument */
+    SVX_ERR_CUDA = -2,         /* CUDA runtime / driver failure (message has the detail) */
+    SVX_ERR_NOMEM = -3,
+    SVX_ERR_UNSUPPORTED = -4   /* e.g. device is not sm_100 */
+} svx_status;
+
+/* element type of images written by svx_encode / read by svx_forward */
+typedef enum {
+    SVX_IMAGE_F32 = 0,         /* float32 NHWC [n][227][227][3]: what next_batch() yields and TF
+                                  receives (create_batch.py:147-152, predict.py:167) */
+    SVX_IMAGE_F16 = 1          /* IEEE half NHWC, same values (lossless: 2 levels per channel) */
+} svx_image_dtype;
+
+/* numeric recipe of the tensor-core layers */
+typedef enum {
+    SVX_PRECISION_3PASS = 0,   /* fp16 hi/lo split operands, 3 MMAs per product: parity default */
+    SVX_PRECISION_1PASS = 1    /* single fp16 pass: reported for comparison only */
+} svx_precision;
+
+/* The reference's 16 TensorFlow variables (src/network/alexnet.py:113-116,141-145), host
+ * float32, TF layouts: conv weights [kh][kw][Cin/groups][Cout], fc weights [in][out]. */
+typedef struct {
+    const float *conv1_w, *conv1_b;   /* [11][11][3][96],    [96]   */
+    const float *conv2_w, *conv2_b;   /* [5][5][48][256],    [256]  groups=2 */
+    const float *conv3_w, *conv3_b;   /* [3][3][256][384],   [384]  */
+    const float *conv4_w, *conv4_b;   /* [3][3][192][384],   [384]  groups=2 */
+    const float *conv5_w, *conv5_b;   /* [3][3][192][256],   [256]  groups=2 */
+    const float *fc6_w, *fc6_b;       /* [9216][4096],       [4096] */
+    const float *fc7_w, *fc7_b;       /* [4096][4096],       [4096] */
+    const float *fc8_w, *fc8_b;       /* [4096][5],          [5]    */
+} svx_weights;
+
+typedef struct svx_handle svx_handle;
+
+/* Replaces Predict.run's model setup (src/network/predict.py:155-189: graph build +
+ * Saver.restore).  `weights` may be NULL for an encoder-only handle.  `max_batch` is the
+ * micro-batch (sites resident on the device at once; workspaces are sized for it). */
+int svx_create(const svx_weights *weights, int device, int64_t max_batch, int precision,
+               svx_handle **out);
+void svx_destroy(svx_handle *h);
+
+/* Replaces BatchGenerator.next_batch's per-image work (create_batch.py:103-152 ->
+ * plot_segment.py:9-73): rows_dev int32[n][12] -> images_dev NHWC [n][227][227][3] of `dtype`.
+ * Any n; asynchronous on `stream`. */
+int svx_encode(svx_handle *h, const int32_t *rows_dev, int64_t n, void *images_dev, int dtype,
+               void *stream);
+
+/* Replaces sess.run(score) (predict.py:209 -> alexnet.py:26-58) on caller-provided images:
+ * images_dev NHWC [n][227][227][3] of `dtype` -> logits_dev float32[n][5]. */
+int svx_forward(svx_handle *h, const void *images_dev, int dtype, int64_t n, float *logits_dev,
+                void *stream);
+
+/* The fused hot path on device buffers: rows_dev -> labels_dev int32[n] (argmax, predict.py:209),
+ * probs_dev float32[n][5] (softmax), logits_dev float32[n][5] (may be NULL).  Images never
+ * leave the device and are written once, in the conv1 operand layout.  Asynchronous. */
+int svx_classify_device(svx_handle *h, const int32_t *rows_dev, int64_t n, int32_t *labels_dev,
+                        float *probs_dev, float *logits_dev, void *stream);
+
+/* The same path on HOST buffers (what a reference-side caller holds): copies rows to the
+ * device, runs, copies labels/probs back, synchronises.  rows_host should be pinned for speed. */
+int svx_classify(svx_handle *h, const int32_t *rows_host, int64_t n, int32_t *labels_host,
+                 float *probs_host);
+
+/* Parity/debug: copy the activation named `name` of the LAST micro-batch (first `n` sites) to
+ * host as float32, NHWC, valid positions only.  Names: "conv1" [55][55][96], "norm1"
+ * [27][27][96], "conv2" [27][27][256], "norm2" [13][13][256], "conv3"/"conv4" [13][13][384],
+ * "conv5" [13][13][256], "pool5" [6][6][256], "fc6"/"fc7" [4096]. */
+int svx_debug_activation(svx_handle *h, const char *name, int64_t n, float *out_host);
+
+/* Standalone tcgen05 GEMM self-test entry (used by tests): C[M][N] = A[M][K] * B[N][K]^T with
+ * fp16 hi/lo operands given as float32 on the device; returns float32 C on the device. */
+int svx_gemm_selftest(int device, const float *a_dev, const float *b_dev, float *c_dev,
+                      int64_t m, int64_t n, int64_t k, int block_n, int precision, void *stream);
+
+/* Kernels launched by this library on the calling thread since the last reset (bench.py's
+ * `gpu_launches`). */
+int64_t svx_launch_count(void);
+void svx_launch_count_reset(void);
+
+int64_t svx_max_batch(const svx_handle *h);
+int svx_device(const svx_handle *h);
+const char *svx_last_error(void);
+const char *svx_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SVX_H_ */
