@@ -1,0 +1,368 @@
+#!/usr/bin/env python3
+"""Benchmark of the SVision encode+classify hot path (BASELINE.json: candidate SV sites/sec).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+A *step* is one pass of the hot path over one batch of synthetic candidate sites: packed
+``int32[n,12]`` rows -> 227x227x3 similarity images (never leaving the device) -> AlexNet ->
+per-site (label, softmax).  Workload at N=1 = BASELINE.json ``configs[1]``: 10 000 synthetic
+sites (set P1, seed 20261017).  With N>1 every rank processes its own 10 000
+sites (weak scaling, sites are independent) and the step ends with ONE all-gather of the
+per-site (label, score) pairs, 8 B/site, as the north-star prescribes.
+
+Printed JSON (one line, rank 0): the driver contract plus
+  * ``value``  : sites/s with the rows already resident in HBM (CUDA events, max over ranks),
+  * ``e2e``    : the same metric through the host entry ``Classifier.classify`` (C-ABI
+                 ``svx_classify``): pinned host rows -> H2D -> kernels -> D2H labels+probs,
+  * ``roofline``: the tensor-core layer kernel (conv1..fc7 launches), algorithmic FLOPs / live
+                 CUDA-event time, against the measured bf16 peak of MEASURED_PEAKS.json,
+  * ``cpu_baseline``: the oracle port (C encoder + torch-CPU AlexNet restatement; TensorFlow
+                 1.14 is not installable here) on a bounded sample, on this box's host cores.
+``--impl reference`` times that CPU path alone (the reference arm).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "candidate SV sites/sec (encode+CNN)"
+UNIT = "sites/s"
+SITES_PER_GPU = 10_000
+MICRO_BATCH = 2048
+CNN_FLOP_PER_SITE = 1_440_662_592            # SURVEY.md §8(a) layer table (2 x 720 331 296 MACs)
+FC8_FLOP_PER_SITE = 2 * 20_480               # runs on CUDA cores, not in the tensor-core kernel
+ENC_BYTES_PER_SITE = 48 + 227 * 227 * 3 * 2  # 16-bit image is what is emitted
+#: algorithmic FLOPs per site of each tensor-core layer (groups honoured, no padding credit)
+LAYER_FLOP = {"conv1": 2 * 105_415_200, "conv2": 2 * 223_948_800, "conv3": 2 * 149_520_384,
+              "conv4": 2 * 112_140_288, "conv5": 2 * 74_760_192, "fc6": 2 * 37_748_736,
+              "fc7": 2 * 16_777_216}
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return {"hbm_gbs": p["hbm_gbs"], "bf16_tflops": p["bf16_tflops"],
+                "bf16_tflops_sustained": p.get("bf16_tflops_sustained", p["bf16_tflops"]),
+                "source": "measured (MEASURED_PEAKS.json)"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0,
+            "source": "fallback (B200_PROFILING.md)"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons DURING the timed region (profiling recipe)."""
+
+    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+              "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            f = tempfile.NamedTemporaryFile("w", suffix=".csv", delete=False)
+            self.path = f.name
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                 "-lms", "100", "-i", str(self.gpu)], stdout=f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self) -> dict:
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        try:
+            self.proc.terminate()
+            self.proc.wait(timeout=5)
+        except Exception:
+            pass
+        try:
+            sm, mx, reasons = [], [], set()
+            for line in open(self.path):
+                c = [x.strip() for x in line.split(",")]
+                if len(c) < 9:
+                    continue
+                try:
+                    sm.append(float(c[1]))
+                    mx.append(float(c[2]))
+                except ValueError:
+                    continue
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown",
+                                    "sw_power_cap"), c[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            os.unlink(self.path)
+            if sm:
+                out = {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)),
+                       "reasons": sorted(reasons), "samples": len(sm)}
+        except Exception:
+            pass
+        return out
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU baseline = the oracle port of the reference's path on this box's host cores
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_rate(rows: np.ndarray, weights, batch: int = 128):
+    """Times encode (C oracle, all threads) + CNN (torch-CPU fp32 restatement, all threads) over
+    `rows`, batch by batch as src/network/predict.py:206-210 does.  Returns (sites/s, seconds)."""
+    import torch
+    from oracle import alexnet, encoder_c
+    torch.set_num_threads(os.cpu_count() or 1)
+    encoder_c.set_threads(os.cpu_count() or 1)
+    t0 = time.perf_counter()
+    for s in range(0, rows.shape[0], batch):
+        imgs = encoder_c.encode_f32(rows[s:s + batch])
+        logits = alexnet.forward(imgs, weights, torch.float32)
+        torch.softmax(logits, 1), torch.argmax(logits, 1)
+    dt = time.perf_counter() - t0
+    return rows.shape[0] / dt, dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    from oracle import encoder_c
+    from svision_b200 import sites, weights
+    encoder_c.build()
+    w = weights.synthetic_weights()
+    sample = int(os.environ.get("SVX_REF_SAMPLE", 256))
+    rows = sites.make_sites_p1(SITES_PER_GPU, seed=sites.SEED_CONFIG2)
+    for i in range(args.warmup):
+        cpu_reference_rate(rows[:sample], w)
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        o = ((i * sample) % (SITES_PER_GPU - sample))
+        cpu_reference_rate(rows[o:o + sample], w)
+    dt = time.perf_counter() - t0
+    value = args.steps * sample / dt
+    cores = os.cpu_count() or 1
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": "configs[1]: synthetic 10k candidate sites (set P1, seed 20261017), "
+                               "227x227x3 images, encode+CNN",
+                   "step": f"bounded sample of {sample} sites of that workload per step"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{sample} sites/step x {args.steps} steps; C restatement of the "
+                                   "encoder + torch-CPU fp32 restatement of alexnet.py (proxy for "
+                                   "TensorFlow 1.14 CPU, not installable here)"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+    from svision_b200 import classifier as C, sites, weights
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the product path has no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    w = weights.synthetic_weights()
+    clf = C.Classifier(w, device=local, max_batch=MICRO_BATCH, precision=args.precision)
+    n = SITES_PER_GPU
+    rows_all = sites.make_sites_p1(n * world, seed=sites.SEED_CONFIG2)
+    rows = np.ascontiguousarray(rows_all[rank * n:(rank + 1) * n])       # contiguous shard
+    rows_dev = clf.rows_to_device(rows)
+    rows_pinned = torch.from_numpy(rows).pin_memory()
+    labels_host = torch.empty((n,), dtype=torch.int32).pin_memory()
+    probs_host = torch.empty((n, 5), dtype=torch.float32).pin_memory()
+    gathered = torch.empty((world * n, 2), dtype=torch.float32, device=dev) if world > 1 else None
+
+    def finish(labels, probs):
+        """(label, score) per site, all-gathered across ranks: predict.py consumes exactly
+        predict_value[i] and softmax_value[i][predict_value[i]] (predict.py:230,251)."""
+        score = probs.gather(1, labels.long().unsqueeze(1)).squeeze(1)
+        pair = torch.stack([labels.float(), score], dim=1)
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, pair)
+            return gathered
+        return pair
+
+    def step_device():
+        labels, probs = clf.classify_device(rows_dev)
+        return finish(labels, probs)
+
+    def step_e2e():
+        l, p = clf.classify(rows_pinned.numpy(), labels_host.numpy(), probs_host.numpy())
+        if world > 1:
+            pair = torch.stack([labels_host.float(), probs_host.gather(
+                1, labels_host.long().unsqueeze(1)).squeeze(1)], dim=1).to(dev, non_blocking=True)
+            dist.all_gather_into_tensor(gathered, pair)
+            torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- warm-up (>= 3) --------------------------------------------------------------------------
+    for _ in range(max(args.warmup, 3)):
+        step_device()
+    step_e2e()
+    barrier()
+
+    # ---- timed: device-resident inputs --------------------------------------------------------------
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    clf.set_profiling(True)
+    clf.profile_read(reset=True)
+    C.launch_count(reset=True)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step_device()
+    e1.record()
+    barrier()
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    launches = C.launch_count()
+    prof = clf.profile_read(reset=True)
+    clf.set_profiling(False)
+
+    # ---- timed: end to end through the host entry ---------------------------------------------------
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_e2e()
+    barrier()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    clocks = sampler.stop() if rank == 0 else {}
+
+    # ---- parity spot check of what was timed (not timed itself) -------------------------------------
+    l_dev, p_dev = clf.classify_device(rows_dev[:256])
+    torch.cuda.synchronize()
+    same = bool((l_dev.cpu() == labels_host[:256]).all()) and bool(
+        torch.equal(p_dev.cpu(), probs_host[:256]))
+
+    if rank == 0:
+        peaks = load_peaks()
+        total_sites = n * world * args.steps
+        value = total_sites / (ms_total * 1e-3)
+        gemm_slots = ("conv1", "conv2", "conv3", "conv4", "conv5", "fc6", "fc7")
+        gemm_ms = sum(prof[k][0] for k in gemm_slots)
+        gemm_launches = sum(prof[k][1] for k in gemm_slots)
+        sites_rank = n * args.steps
+        flops = (CNN_FLOP_PER_SITE - FC8_FLOP_PER_SITE) * sites_rank
+        achieved = flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
+        peak = peaks["bf16_tflops_sustained"]
+        enc_ms = prof["encode"][0]
+        enc_gbs = ENC_BYTES_PER_SITE * sites_rank / (enc_ms * 1e-3) / 1e9 if enc_ms > 0 else 0.0
+        layers = {}
+        for k in C.Classifier.PROFILE_SLOTS:
+            ms, cnt = prof[k]
+            entry = {"ms_per_launch": ms / cnt if cnt else None, "launches": cnt,
+                     "share": ms / (ms_total) if ms_total > 0 else None}
+            if k in LAYER_FLOP and ms > 0:
+                entry["tflops_algorithmic"] = LAYER_FLOP[k] * sites_rank / (ms * 1e-3) / 1e12
+            layers[k] = entry
+        # CPU baseline on a bounded sample (rank 0, N=1 only)
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            from oracle import encoder_c
+            encoder_c.build()
+            sample = int(os.environ.get("SVX_REF_SAMPLE", 512))
+            cpu_reference_rate(rows[:128], w)
+            rate, secs = cpu_reference_rate(rows[:sample], w)
+            cpu = {"value": rate, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port",
+                   "sample": f"first {sample} sites of the workload, {secs:.1f} s; C restatement of "
+                             "the encoder + torch-CPU fp32 restatement of alexnet.py (proxy for "
+                             "TensorFlow 1.14 CPU, not installable here)"}
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f16x3 (fp16 hi/lo split operands, fp32 accumulate)" if args.precision == "3pass"
+                     else "f16 (single pass; NOT parity-clean)",
+            "data": "synthetic",
+            "config": {"workload": "configs[1]: synthetic 10k candidate sites per GPU (set P1, seed "
+                                   "20261017), 227x227x3 images, encode+CNN",
+                       "sites_per_gpu": n, "micro_batch": MICRO_BATCH, "precision": args.precision,
+                       "weights": "synthetic He-init, calibrated fc8 (seed 1234)",
+                       "collective": "all_gather of (label, score), 8 B/site" if world > 1 else "none",
+                       "l2": "activation working set per micro-batch ~8 GB and fp16 hi/lo weights "
+                             "228 MB both exceed the 126 MB L2; no flush needed"},
+            "e2e": {"value": total_sites / e2e_s, "unit": UNIT,
+                    "h2d_bytes_per_step": int(n * world * 48),
+                    "d2h_bytes_per_step": int(n * world * 24)},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": {"kernel": "gemm_tc_kernel (tcgen05 layer kernel: conv1..conv5, fc6, fc7)",
+                         "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                         "frac": achieved / peak if peak else None, "traffic": None,
+                         "peak_source": peaks["source"] + ", bf16 sustained",
+                         "launches": gemm_launches,
+                         "share_of_step": gemm_ms / ms_total if ms_total > 0 else None,
+                         "note": "3-pass parity recipe executes ~3x (conv1 2x) the algorithmic "
+                                 "FLOPs plus layout padding; frac counts algorithmic FLOPs only"},
+            "encoder": {"bound": "hbm", "achieved": enc_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                        "frac": enc_gbs / peaks["hbm_gbs"],
+                        "note": "conv1-operand layout (space-to-depth, 64-ch padded): writes 416 KB/"
+                                "site for 309 KB algorithmic"},
+            "layers": layers,
+            "cpu_baseline": cpu,
+            "parity_spot_check": "device and host entries agree bit-for-bit on 256 sites" if same
+                                 else "MISMATCH between device and host entries",
+        }
+        print(json.dumps(line), flush=True)
+    clf.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--precision", default="3pass", choices=["3pass", "1pass"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_gpu(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -114,6 +114,15 @@ int svx_debug_activation(svx_handle *h, const char *name, int64_t n, float *out_
 int svx_gemm_selftest(int device, const float *a_dev, const float *b_dev, float *c_dev,
                       int64_t m, int64_t n, int64_t k, int block_n, int precision, void *stream);
 
+/* Per-kernel device timing with CUDA events recorded on the launching stream (bench.py's live
+ * roofline numbers).  Slots: 0 encode, 1 conv1, 2 pool1+lrn1, 3 conv2, 4 pool2+lrn2, 5 conv3,
+ * 6 conv4, 7 conv5, 8 pool5, 9 fc6, 10 fc7, 11 fc8+softmax.  svx_profile_read synchronises,
+ * adds the elapsed milliseconds and launch counts since the last reset into ms_out[12] /
+ * launches_out[12] (either may be NULL) and optionally resets. */
+#define SVX_PROFILE_SLOTS 12
+int svx_set_profiling(svx_handle *h, int enable);
+int svx_profile_read(svx_handle *h, float *ms_out, int64_t *launches_out, int reset);
+
 /* Kernels launched by this library on the calling thread since the last reset (bench.py's
  * `gpu_launches`). */
 int64_t svx_launch_count(void);

@@ -1,0 +1,237 @@
+// CUDA-core kernels around the tensor-core layers: max-pool (+LRN), fc8 + softmax + argmax,
+// and the layout/precision converters.
+//
+// Replaces (reference): src/network/alexnet.py:158-166 (`max_pool` 3x3/2 VALID, `lrn` radius 2,
+// alpha 2e-5, beta 0.75, bias 1), :58 fc8 (`xw_plus_b`, no ReLU), and
+// src/network/predict.py:209 (`tf.argmax(score, 1)`, `tf.nn.softmax(score)`).
+#include "common.cuh"
+#include "kernels.h"
+
+#include <math_constants.h>
+
+namespace svx {
+
+namespace {
+
+__device__ __forceinline__ void split_store(float v, __half* hi, __half* lo, long long idx) {
+    const __half h = __float2half_rn(v);
+    hi[idx] = h;
+    lo[idx] = __float2half_rn(v - __half2float(h));
+}
+
+// One warp per output position; lane l owns CPL consecutive channels (16-byte loads), so the
+// LRN window (c-2..c+2) needs only the two edge values of each neighbouring lane (shuffles).
+template <int CPL>
+__global__ void __launch_bounds__(256) pool_kernel(const PoolParams p, long long total_pos) {
+    const int lane = threadIdx.x & 31;
+    const int warps_per_block = blockDim.x >> 5;
+    const long long warp0 = (long long)blockIdx.x * warps_per_block + (threadIdx.x >> 5);
+    const long long nwarps = (long long)gridDim.x * warps_per_block;
+    const int per_img = p.out_h * p.out_w;
+    const int c0 = lane * CPL;
+    const bool active = c0 < p.C;
+    for (long long pos = warp0; pos < total_pos; pos += nwarps) {
+        const long long img = pos / per_img;
+        const int rem = (int)(pos - img * per_img);
+        const int y = rem / p.out_w, x = rem - y * p.out_w;
+        float m[CPL];
+#pragma unroll
+        for (int j = 0; j < CPL; ++j) m[j] = active ? -CUDART_INF_F : 0.f;
+        if (active) {
+            const float* base =
+                p.in + ((img * p.in_pos_per_img + (long long)(2 * y) * p.in_grid_w + 2 * x) * p.C + c0);
+#pragma unroll
+            for (int i = 0; i < 3; ++i)
+#pragma unroll
+                for (int j = 0; j < 3; ++j) {
+                    const float4* q = reinterpret_cast<const float4*>(
+                        base + (long long)(i * p.in_grid_w + j) * p.C);
+#pragma unroll
+                    for (int v = 0; v < CPL / 4; ++v) {
+                        const float4 t = __ldg(q + v);
+                        m[4 * v + 0] = fmaxf(m[4 * v + 0], t.x);
+                        m[4 * v + 1] = fmaxf(m[4 * v + 1], t.y);
+                        m[4 * v + 2] = fmaxf(m[4 * v + 2], t.z);
+                        m[4 * v + 3] = fmaxf(m[4 * v + 3], t.w);
+                    }
+                }
+        }
+        float out[CPL];
+        if (p.lrn) {
+            float sq[CPL + 4];
+#pragma unroll
+            for (int j = 0; j < CPL; ++j) sq[j + 2] = m[j] * m[j];
+            // neighbours' edge squares (inactive lanes hold zeros = the zero padding of the window)
+            const float l0 = __shfl_up_sync(0xffffffffu, sq[CPL], 1);       // lane-1's channel CPL-2
+            const float l1 = __shfl_up_sync(0xffffffffu, sq[CPL + 1], 1);   // lane-1's channel CPL-1
+            const float r0 = __shfl_down_sync(0xffffffffu, sq[2], 1);       // lane+1's channel 0
+            const float r1 = __shfl_down_sync(0xffffffffu, sq[3], 1);       // lane+1's channel 1
+            sq[0] = lane > 0 ? l0 : 0.f;
+            sq[1] = lane > 0 ? l1 : 0.f;
+            sq[CPL + 2] = lane < 31 ? r0 : 0.f;
+            sq[CPL + 3] = lane < 31 ? r1 : 0.f;
+#pragma unroll
+            for (int j = 0; j < CPL; ++j) {
+                const float s5 = sq[j] + sq[j + 1] + sq[j + 2] + sq[j + 3] + sq[j + 4];
+                out[j] = m[j] * powf(1.0f + 2e-5f * s5, -0.75f);
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < CPL; ++j) out[j] = m[j];
+        }
+        if (active) {
+            long long o;
+            if (p.flatten) {
+                o = img * (long long)p.out_ld + (long long)(y * p.out_w + x) * p.C + c0;
+            } else {
+                const int col = (c0 / p.group_real) * p.group_pad + (c0 % p.group_real);
+                o = (img * p.out_pos_per_img + (long long)y * p.out_grid_w + x) * p.out_ld + col;
+            }
+            uint32_t ph[CPL / 2], pl[CPL / 2];
+#pragma unroll
+            for (int j = 0; j < CPL / 2; ++j) {
+                const __half h0 = __float2half_rn(out[2 * j]), h1 = __float2half_rn(out[2 * j + 1]);
+                const __half e0 = __float2half_rn(out[2 * j] - __half2float(h0));
+                const __half e1 = __float2half_rn(out[2 * j + 1] - __half2float(h1));
+                ph[j] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
+                pl[j] = (uint32_t)__half_as_ushort(e0) | ((uint32_t)__half_as_ushort(e1) << 16);
+            }
+            if constexpr (CPL == 4) {
+                *reinterpret_cast<uint2*>(p.out_hi + o) = make_uint2(ph[0], ph[1]);
+                *reinterpret_cast<uint2*>(p.out_lo + o) = make_uint2(pl[0], pl[1]);
+            } else {
+                *reinterpret_cast<uint4*>(p.out_hi + o) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+                *reinterpret_cast<uint4*>(p.out_lo + o) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+            }
+        }
+    }
+}
+
+// One warp per site.
+__global__ void __launch_bounds__(256)
+fc8_softmax_kernel(const __half* __restrict__ x_hi, const __half* __restrict__ x_lo,
+                   const float* __restrict__ w8, const float* __restrict__ b8, long long n,
+                   int32_t* __restrict__ labels, float* __restrict__ probs,
+                   float* __restrict__ logits) {
+    const int lane = threadIdx.x & 31;
+    const long long site = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (site >= n) return;
+    const __half* xh = x_hi + site * 4096;
+    const __half* xl = x_lo + site * 4096;
+    float acc[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int i = 0; i < 128; ++i) {
+        const int k = lane + 32 * i;
+        const float x = __half2float(xh[k]) + __half2float(xl[k]);
+        const float* w = w8 + k * 5;
+#pragma unroll
+        for (int j = 0; j < 5; ++j) acc[j] = fmaf(x, __ldg(w + j), acc[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < 5; ++j)
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], off);
+    if (lane == 0) {
+        float l[5], mx = -CUDART_INF_F;
+        int arg = 0;
+#pragma unroll
+        for (int j = 0; j < 5; ++j) {
+            l[j] = acc[j] + b8[j];
+            if (l[j] > mx) { mx = l[j]; arg = j; }       // first maximum, like tf.argmax
+        }
+        float e[5], s = 0.f;
+#pragma unroll
+        for (int j = 0; j < 5; ++j) { e[j] = expf(l[j] - mx); s += e[j]; }
+        labels[site] = arg;
+#pragma unroll
+        for (int j = 0; j < 5; ++j) {
+            probs[site * 5 + j] = e[j] / s;
+            if (logits) logits[site * 5 + j] = l[j];
+        }
+    }
+}
+
+template <typename T>
+__global__ void nhwc_to_s2d_kernel(const T* __restrict__ img, long long n, __half* __restrict__ out) {
+    constexpr int S2D = 57, IMG = 227;
+    const long long total = n * S2D * S2D * 8;
+    for (long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x; v < total;
+         v += (long long)gridDim.x * blockDim.x) {
+        const int q = (int)(v & 7);
+        const long long sp_all = v >> 3;
+        const long long im = sp_all / (S2D * S2D);
+        const int sp = (int)(sp_all - im * (S2D * S2D));
+        const int Y = sp / S2D, X = sp - Y * S2D;
+        uint32_t h[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int k = 8 * q + j;
+            float val = 0.f;
+            if (k < 48) {
+                const int d = k / 3, ch = k - 3 * d;
+                const int r = 4 * Y + (d >> 2), c = 4 * X + (d & 3);
+                if (r < IMG && c < IMG)
+                    val = (float)img[(im * IMG * IMG + (long long)r * IMG + c) * 3 + ch];
+            }
+            h[j] = __half_as_ushort(__float2half_rn(val));
+        }
+        reinterpret_cast<uint4*>(out)[v] =
+            make_uint4(h[0] | (h[1] << 16), h[2] | (h[3] << 16), h[4] | (h[5] << 16), h[6] | (h[7] << 16));
+    }
+}
+
+__global__ void split_hilo_kernel(const float* __restrict__ in, long long count,
+                                  __half* __restrict__ hi, __half* __restrict__ lo) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < count;
+         i += (long long)gridDim.x * blockDim.x)
+        split_store(in[i], hi, lo, i);
+}
+
+}  // namespace
+
+int launch_pool(const PoolParams& p, long long n_img, int num_sms, cudaStream_t stream) {
+    const long long total = n_img * p.out_h * p.out_w;
+    if (total <= 0) return 0;
+    const int cpl = p.C <= 128 ? 4 : 8;
+    if (p.C % cpl != 0 || p.C / cpl > 32 || p.group_real % cpl != 0 || p.group_pad % cpl != 0)
+        return fail(-1, "pool: unsupported channel count / grouping");
+    long long blocks = (long long)num_sms * 8;           // 8 CTAs x 8 warps resident per SM
+    if (blocks > (total + 7) / 8) blocks = (total + 7) / 8;
+    if (cpl == 4) pool_kernel<4><<<(unsigned)blocks, 256, 0, stream>>>(p, total);
+    else          pool_kernel<8><<<(unsigned)blocks, 256, 0, stream>>>(p, total);
+    SVX_LAUNCH_CHECK("pool_kernel");
+    return 0;
+}
+
+int launch_fc8_softmax(const __half* x_hi, const __half* x_lo, const float* w8, const float* b8,
+                       long long n, int32_t* labels, float* probs, float* logits,
+                       cudaStream_t stream) {
+    if (n <= 0) return 0;
+    fc8_softmax_kernel<<<(unsigned)((n + 7) / 8), 256, 0, stream>>>(x_hi, x_lo, w8, b8, n, labels,
+                                                                     probs, logits);
+    SVX_LAUNCH_CHECK("fc8_softmax_kernel");
+    return 0;
+}
+
+int launch_nhwc_to_s2d(const void* images, int dtype, long long n, __half* out, cudaStream_t stream) {
+    if (n <= 0) return 0;
+    const long long total = n * 57 * 57 * 8;
+    const unsigned blocks = (unsigned)((total + 255) / 256 > 148 * 16 ? 148 * 16 : (total + 255) / 256);
+    if (dtype == 0)
+        nhwc_to_s2d_kernel<float><<<blocks, 256, 0, stream>>>(static_cast<const float*>(images), n, out);
+    else if (dtype == 1)
+        nhwc_to_s2d_kernel<__half><<<blocks, 256, 0, stream>>>(static_cast<const __half*>(images), n, out);
+    else
+        return fail(-1, "nhwc_to_s2d: bad dtype");
+    SVX_LAUNCH_CHECK("nhwc_to_s2d_kernel");
+    return 0;
+}
+
+int launch_split_hilo(const float* in, long long count, __half* hi, __half* lo, cudaStream_t stream) {
+    if (count <= 0) return 0;
+    const unsigned blocks = (unsigned)((count + 255) / 256 > 148 * 16 ? 148 * 16 : (count + 255) / 256);
+    split_hilo_kernel<<<blocks, 256, 0, stream>>>(in, count, hi, lo);
+    SVX_LAUNCH_CHECK("split_hilo_kernel");
+    return 0;
+}
+
+}  // namespace svx

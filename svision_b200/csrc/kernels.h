@@ -1,0 +1,82 @@
+// Internal launcher interface between the C-ABI (svx_api.cu) and the kernels.
+#pragma once
+
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace svx {
+
+// ---- encoder.cu -------------------------------------------------------------------------------
+// mode 0: NHWC fp32, 1: NHWC fp16, 2: conv1 operand layout [n][57*57][64] fp16
+int launch_encode(const int32_t* rows_dev, long long n, void* out, int mode, int num_sms,
+                  cudaStream_t stream);
+
+// ---- gemm_tc.cu -------------------------------------------------------------------------------
+constexpr int GEMM_BLOCK_M = 128;
+constexpr int GEMM_BLOCK_K = 64;
+constexpr int GEMM_MAX_TAPS = 25;
+
+// One tensor-core layer expressed as a "shifted GEMM":
+//   D[m, g*Ng + n] = sum_t sum_c  A[m + row_off[t], g*a_group_cols + c] * W[g*Ng + n, t*Cg + c]
+// A: [rows_a][lda] fp16 (hi and lo planes), W: [n_total][k_total] fp16 K-major (hi, lo planes).
+struct GemmLayer {
+    CUtensorMap tm_a_hi, tm_a_lo, tm_b_hi, tm_b_lo;
+    int block_n;               // 64 / 96 / 128
+    int chunk_kblocks;         // k-blocks accumulated in TMEM before promotion to fp32 registers
+    int groups;                // 1 or 2
+    int n_per_group;           // output channels per group (multiple of block_n)
+    int taps;                  // filter taps (1 for fc)
+    int cblocks;               // 64-wide channel blocks per tap
+    int a_group_cols;          // column offset of group g in A
+    int row_off[GEMM_MAX_TAPS];
+    int use_a_lo, use_b_lo;    // which hi/lo cross terms are issued (3-pass / 2-pass / 1-pass)
+    long long m_rows;          // rows of D actually computed (and of A addressable)
+    // epilogue: bias + optional ReLU, then either fp32 or fp16 hi/lo planes
+    const float* bias;         // [groups * n_per_group]
+    int relu;
+    float* out_f32;            // [m_rows][ldc] or nullptr
+    __half* out_hi;            // [m_rows][ldc] or nullptr
+    __half* out_lo;
+    int ldc;
+    // valid-row mask for padded spatial layouts: row m is stored iff
+    //   (m % pos_per_img) / grid_w < valid_h  &&  (m % pos_per_img) % grid_w < valid_w
+    // pos_per_img == 0 disables the mask.
+    int pos_per_img, grid_w, valid_h, valid_w;
+};
+
+int launch_gemm_layer(const GemmLayer& L, int num_sms, cudaStream_t stream);
+
+// Builds a 2-D tiled fp16 tensor map (SWIZZLE_128B, box = {64, box_rows}) over a row-major
+// [rows][cols] matrix with leading dimension ld (elements).
+int make_tensor_map_2d(CUtensorMap* tm, const void* base, long long rows, long long cols,
+                       long long ld, int box_rows);
+
+// ---- cnn_aux.cu -------------------------------------------------------------------------------
+struct PoolParams {
+    const float* in;           // [n*in_pos_per_img][C] fp32 (post-ReLU conv output)
+    int in_grid_w, in_pos_per_img;
+    int C;
+    int out_h, out_w;          // pooled size
+    int lrn;                   // apply LRN(radius 2, alpha 2e-5, beta .75, bias 1) after pooling
+    __half* out_hi;
+    __half* out_lo;
+    int out_ld;                // leading dimension of the output rows (elements)
+    int out_grid_w, out_pos_per_img;   // output row = img*out_pos_per_img + y*out_grid_w + x
+    int group_real, group_pad; // output column of channel c = (c / group_real)*group_pad + c % group_real
+    int flatten;               // 1: output is [n][out_h*out_w*C] (NHWC flatten for fc6)
+};
+int launch_pool(const PoolParams& p, long long n_img, int num_sms, cudaStream_t stream);
+
+// logits = (x_hi + x_lo) @ W8 + b8 ; labels = argmax ; probs = softmax   (fp32, CUDA cores)
+int launch_fc8_softmax(const __half* x_hi, const __half* x_lo, const float* w8 /*[4096][5]*/,
+                       const float* b8, long long n, int32_t* labels, float* probs, float* logits,
+                       cudaStream_t stream);
+
+// NHWC [n][227][227][3] (fp32 or fp16) -> conv1 operand layout [n][57*57][64] fp16
+int launch_nhwc_to_s2d(const void* images, int dtype, long long n, __half* out, cudaStream_t stream);
+
+// float32 -> fp16 hi/lo planes (self-test helper)
+int launch_split_hilo(const float* in, long long count, __half* hi, __half* lo, cudaStream_t stream);
+
+}  // namespace svx

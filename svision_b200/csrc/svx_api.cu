@@ -1,0 +1,573 @@
+// C-ABI of libsvx (see include/svx.h): handle, one-time weight repack, HBM workspaces, the
+// per-micro-batch kernel sequence.  Host code here is plumbing; all arithmetic on the path runs in
+// the kernels of encoder.cu / gemm_tc.cu / cnn_aux.cu.
+#include "../../include/svx.h"
+
+#include "common.cuh"
+#include "kernels.h"
+
+#include <cstring>
+#include <memory>
+#include <utility>
+#include <vector>
+
+namespace svx {
+
+static thread_local std::string g_error;
+static thread_local long long g_launches = 0;
+
+void set_error(const std::string& msg) { g_error = msg; }
+int fail(int code, const std::string& msg) {
+    g_error = msg;
+    return code;
+}
+void count_launch(int n) { g_launches += n; }
+
+// ---- geometry of the padded activation layouts (DESIGN.md "HBM layouts") ----------------------
+constexpr int S2D = 57;                       // conv1 input grid (228/4), outputs valid on 55x55
+constexpr int P1 = S2D * S2D;                 // 3249 positions per site in x1 / y1
+constexpr int G2 = 29, P2 = G2 * G2;          // conv2 grid: 27 + 2 shared pad rows/cols -> 841
+constexpr int G3 = 14, P3 = G3 * G3;          // conv3-5 grid: 13 + 1 -> 196
+
+constexpr int kChunkKBlocks = 4;              // K = 256 per TMEM accumulation chain
+
+enum { L_CONV1 = 0, L_CONV2, L_CONV3, L_CONV4, L_CONV5, L_FC6, L_FC7, L_COUNT };
+
+struct LayerSpec {
+    int taps, cg_real, cg_pad, groups, n_total, block_n, kh, kw;
+};
+static const LayerSpec kSpec[L_COUNT] = {
+    /* conv1 (s2d) */ {9, 48, 64, 1, 96, 96, 3, 3},
+    /* conv2       */ {25, 48, 64, 2, 256, 128, 5, 5},
+    /* conv3       */ {9, 256, 256, 1, 384, 128, 3, 3},
+    /* conv4       */ {9, 192, 192, 2, 384, 96, 3, 3},
+    /* conv5       */ {9, 192, 192, 2, 256, 128, 3, 3},
+    /* fc6         */ {1, 9216, 9216, 1, 4096, 128, 1, 1},
+    /* fc7         */ {1, 4096, 4096, 1, 4096, 128, 1, 1},
+};
+
+}  // namespace svx
+
+using namespace svx;
+
+struct svx_handle {
+    int device = 0;
+    int num_sms = 148;
+    long long max_batch = 0;
+    int precision = 0;
+    bool has_model = false;
+    cudaStream_t stream = nullptr;       // used by svx_classify (host entry)
+    long long last_n = 0;
+
+    std::vector<void*> allocs;
+    __half* w_hi[L_COUNT] = {};
+    __half* w_lo[L_COUNT] = {};
+    float* bias[L_COUNT] = {};
+    float* w8 = nullptr;
+    float* b8 = nullptr;
+
+    __half* x1 = nullptr;                                   // [B*3249][64]
+    float* y1 = nullptr;                                    // [B*3249][96]
+    __half *x2_hi = nullptr, *x2_lo = nullptr;              // [B*841][128]
+    float* y2 = nullptr;                                    // [B*841][256]
+    __half *x3_hi = nullptr, *x3_lo = nullptr;              // [B*196][256]
+    __half *x4_hi = nullptr, *x4_lo = nullptr;              // [B*196][384]
+    __half *x5_hi = nullptr, *x5_lo = nullptr;              // [B*196][384]
+    float* y5 = nullptr;                                    // [B*196][256]
+    __half *x6_hi = nullptr, *x6_lo = nullptr;              // [B][9216]
+    __half *x7_hi = nullptr, *x7_lo = nullptr;              // [B][4096]
+    __half *x8_hi = nullptr, *x8_lo = nullptr;              // [B][4096]
+
+    int32_t* rows_dev = nullptr;                            // staging for the host entry
+    int32_t* labels_dev = nullptr;
+    float* probs_dev = nullptr;
+
+    GemmLayer layer[L_COUNT];
+
+    // optional per-kernel timing (svx_set_profiling)
+    bool profiling = false;
+    std::vector<cudaEvent_t> ev_pool;                       // reusable events
+    std::vector<std::pair<int, cudaEvent_t>> ev_marks;      // (slot or -1 = end of sequence, event)
+    size_t ev_used = 0;
+    double prof_ms[SVX_PROFILE_SLOTS] = {};
+    long long prof_launches[SVX_PROFILE_SLOTS] = {};
+};
+
+namespace {
+
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = true;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) ok = false;
+        if (ok && prev != dev && cudaSetDevice(dev) != cudaSuccess) ok = false;
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+template <typename T>
+int dev_alloc(svx_handle* h, T** p, size_t count, bool zero = true) {
+    void* q = nullptr;
+    size_t bytes = count * sizeof(T);
+    if (bytes == 0) bytes = 16;
+    cudaError_t e = cudaMalloc(&q, bytes);
+    if (e != cudaSuccess)
+        return fail(SVX_ERR_NOMEM, std::string("cudaMalloc(") + std::to_string(bytes) +
+                                       " B): " + cudaGetErrorString(e));
+    h->allocs.push_back(q);
+    if (zero) SVX_CUDA_CHECK(cudaMemset(q, 0, bytes));
+    *p = static_cast<T*>(q);
+    return 0;
+}
+
+// TF-layout weights -> K-major [n_total][taps*cg_pad] fp16 hi/lo planes on the device.
+int upload_layer_weights(svx_handle* h, int li, const float* w_tf, const float* b_tf) {
+    const LayerSpec& s = kSpec[li];
+    const size_t K = (size_t)s.taps * s.cg_pad;
+    const size_t count = (size_t)s.n_total * K;
+    std::vector<__half> hi(count), lo(count);
+    std::memset(hi.data(), 0, count * sizeof(__half));
+    std::memset(lo.data(), 0, count * sizeof(__half));
+    auto put = [&](size_t n, size_t k, float w) {
+        const __half hh = __float2half_rn(w);
+        hi[n * K + k] = hh;
+        lo[n * K + k] = __float2half_rn(w - __half2float(hh));
+    };
+    if (li == L_CONV1) {
+        // 11x11/4 conv as a 3x3/1 conv over the 4x4 space-to-depth image:
+        // tap (a,b), channel (dy*4+dx)*3+c  <-  W[4a+dy][4b+dx][c][n]  (zero beyond 10)
+        for (int a = 0; a < 3; ++a)
+            for (int b = 0; b < 3; ++b)
+                for (int dy = 0; dy < 4; ++dy)
+                    for (int dx = 0; dx < 4; ++dx) {
+                        const int kh = 4 * a + dy, kw = 4 * b + dx;
+                        if (kh > 10 || kw > 10) continue;
+                        for (int c = 0; c < 3; ++c)
+                            for (int n = 0; n < 96; ++n)
+                                put(n, (size_t)(a * 3 + b) * 64 + (dy * 4 + dx) * 3 + c,
+                                    w_tf[((size_t)(kh * 11 + kw) * 3 + c) * 96 + n]);
+                    }
+    } else {
+        for (int t = 0; t < s.taps; ++t)
+            for (int c = 0; c < s.cg_real; ++c) {
+                const float* src = w_tf + ((size_t)t * s.cg_real + c) * s.n_total;
+                for (int n = 0; n < s.n_total; ++n) put(n, (size_t)t * s.cg_pad + c, src[n]);
+            }
+    }
+    int rc;
+    if ((rc = dev_alloc(h, &h->w_hi[li], count, false))) return rc;
+    if ((rc = dev_alloc(h, &h->w_lo[li], count, false))) return rc;
+    if ((rc = dev_alloc(h, &h->bias[li], (size_t)s.n_total, false))) return rc;
+    SVX_CUDA_CHECK(cudaMemcpy(h->w_hi[li], hi.data(), count * sizeof(__half), cudaMemcpyHostToDevice));
+    SVX_CUDA_CHECK(cudaMemcpy(h->w_lo[li], lo.data(), count * sizeof(__half), cudaMemcpyHostToDevice));
+    SVX_CUDA_CHECK(cudaMemcpy(h->bias[li], b_tf, (size_t)s.n_total * sizeof(float), cudaMemcpyHostToDevice));
+    return 0;
+}
+
+int setup_layer(svx_handle* h, int li, const __half* a_hi, const __half* a_lo, long long a_rows,
+                int lda, int grid_w, int center, float* out_f32, __half* out_hi, __half* out_lo,
+                int ldc, int pos_per_img, int valid_h, int valid_w) {
+    const LayerSpec& s = kSpec[li];
+    GemmLayer& L = h->layer[li];
+    std::memset(&L, 0, sizeof(L));
+    const long long K = (long long)s.taps * s.cg_pad;
+    int rc;
+    if ((rc = make_tensor_map_2d(&L.tm_a_hi, a_hi, a_rows, lda, lda, GEMM_BLOCK_M))) return rc;
+    if ((rc = make_tensor_map_2d(&L.tm_a_lo, a_lo ? a_lo : a_hi, a_rows, lda, lda, GEMM_BLOCK_M))) return rc;
+    if ((rc = make_tensor_map_2d(&L.tm_b_hi, h->w_hi[li], s.n_total, K, K, s.block_n))) return rc;
+    if ((rc = make_tensor_map_2d(&L.tm_b_lo, h->w_lo[li], s.n_total, K, K, s.block_n))) return rc;
+    L.block_n = s.block_n;
+    L.chunk_kblocks = kChunkKBlocks;
+    L.groups = s.groups;
+    L.n_per_group = s.n_total / s.groups;
+    L.taps = s.taps;
+    L.cblocks = s.cg_pad / GEMM_BLOCK_K;
+    L.a_group_cols = s.cg_pad;
+    for (int kh = 0; kh < s.kh; ++kh)
+        for (int kw = 0; kw < s.kw; ++kw)
+            L.row_off[kh * s.kw + kw] = (kh - center) * grid_w + (kw - center);
+    const bool three = h->precision == SVX_PRECISION_3PASS;
+    L.use_b_lo = three ? 1 : 0;
+    L.use_a_lo = (three && a_lo != nullptr) ? 1 : 0;
+    L.m_rows = 0;
+    L.bias = h->bias[li];
+    L.relu = 1;
+    L.out_f32 = out_f32;
+    L.out_hi = out_hi;
+    L.out_lo = out_lo;
+    L.ldc = ldc;
+    L.pos_per_img = pos_per_img;
+    L.grid_w = grid_w;
+    L.valid_h = valid_h;
+    L.valid_w = valid_w;
+    return 0;
+}
+
+int build_model(svx_handle* h, const svx_weights* w) {
+    const long long B = h->max_batch;
+    int rc;
+    const float* wt[L_COUNT] = {w->conv1_w, w->conv2_w, w->conv3_w, w->conv4_w, w->conv5_w, w->fc6_w, w->fc7_w};
+    const float* bt[L_COUNT] = {w->conv1_b, w->conv2_b, w->conv3_b, w->conv4_b, w->conv5_b, w->fc6_b, w->fc7_b};
+    for (int li = 0; li < L_COUNT; ++li) {
+        if (!wt[li] || !bt[li]) return fail(SVX_ERR_INVALID, "svx_create: NULL weight pointer");
+        if ((rc = upload_layer_weights(h, li, wt[li], bt[li]))) return rc;
+    }
+    if (!w->fc8_w || !w->fc8_b) return fail(SVX_ERR_INVALID, "svx_create: NULL fc8 pointer");
+    if ((rc = dev_alloc(h, &h->w8, (size_t)4096 * 5, false))) return rc;
+    if ((rc = dev_alloc(h, &h->b8, (size_t)5, false))) return rc;
+    SVX_CUDA_CHECK(cudaMemcpy(h->w8, w->fc8_w, 4096 * 5 * sizeof(float), cudaMemcpyHostToDevice));
+    SVX_CUDA_CHECK(cudaMemcpy(h->b8, w->fc8_b, 5 * sizeof(float), cudaMemcpyHostToDevice));
+
+    // activations: zero once; pad positions/channels are never written afterwards
+    if ((rc = dev_alloc(h, &h->y1, (size_t)B * P1 * 96))) return rc;
+    if ((rc = dev_alloc(h, &h->x2_hi, (size_t)B * P2 * 128))) return rc;
+    if ((rc = dev_alloc(h, &h->x2_lo, (size_t)B * P2 * 128))) return rc;
+    if ((rc = dev_alloc(h, &h->y2, (size_t)B * P2 * 256))) return rc;
+    if ((rc = dev_alloc(h, &h->x3_hi, (size_t)B * P3 * 256))) return rc;
+    if ((rc = dev_alloc(h, &h->x3_lo, (size_t)B * P3 * 256))) return rc;
+    if ((rc = dev_alloc(h, &h->x4_hi, (size_t)B * P3 * 384))) return rc;
+    if ((rc = dev_alloc(h, &h->x4_lo, (size_t)B * P3 * 384))) return rc;
+    if ((rc = dev_alloc(h, &h->x5_hi, (size_t)B * P3 * 384))) return rc;
+    if ((rc = dev_alloc(h, &h->x5_lo, (size_t)B * P3 * 384))) return rc;
+    if ((rc = dev_alloc(h, &h->y5, (size_t)B * P3 * 256))) return rc;
+    if ((rc = dev_alloc(h, &h->x6_hi, (size_t)B * 9216))) return rc;
+    if ((rc = dev_alloc(h, &h->x6_lo, (size_t)B * 9216))) return rc;
+    if ((rc = dev_alloc(h, &h->x7_hi, (size_t)B * 4096))) return rc;
+    if ((rc = dev_alloc(h, &h->x7_lo, (size_t)B * 4096))) return rc;
+    if ((rc = dev_alloc(h, &h->x8_hi, (size_t)B * 4096))) return rc;
+    if ((rc = dev_alloc(h, &h->x8_lo, (size_t)B * 4096))) return rc;
+
+    //                 layer    A hi      A lo      A rows  lda grid center out_f32 out_hi    out_lo   ldc  pos  vh  vw
+    if ((rc = setup_layer(h, L_CONV1, h->x1, nullptr, B * P1, 64, S2D, 0, h->y1, nullptr, nullptr, 96, 0, 0, 0))) return rc;
+    if ((rc = setup_layer(h, L_CONV2, h->x2_hi, h->x2_lo, B * P2, 128, G2, 2, h->y2, nullptr, nullptr, 256, 0, 0, 0))) return rc;
+    if ((rc = setup_layer(h, L_CONV3, h->x3_hi, h->x3_lo, B * P3, 256, G3, 1, nullptr, h->x4_hi, h->x4_lo, 384, P3, 13, 13))) return rc;
+    if ((rc = setup_layer(h, L_CONV4, h->x4_hi, h->x4_lo, B * P3, 384, G3, 1, nullptr, h->x5_hi, h->x5_lo, 384, P3, 13, 13))) return rc;
+    if ((rc = setup_layer(h, L_CONV5, h->x5_hi, h->x5_lo, B * P3, 384, G3, 1, h->y5, nullptr, nullptr, 256, 0, 0, 0))) return rc;
+    if ((rc = setup_layer(h, L_FC6, h->x6_hi, h->x6_lo, B, 9216, 1, 0, nullptr, h->x7_hi, h->x7_lo, 4096, 0, 0, 0))) return rc;
+    if ((rc = setup_layer(h, L_FC7, h->x7_hi, h->x7_lo, B, 4096, 1, 0, nullptr, h->x8_hi, h->x8_lo, 4096, 0, 0, 0))) return rc;
+    h->has_model = true;
+    return 0;
+}
+
+// Record "kernel `slot` starts here" (slot -1 closes a sequence) on the launching stream.
+void mark(svx_handle* h, int slot, cudaStream_t st) {
+    if (!h->profiling) return;
+    if (h->ev_used >= (size_t)1 << 16) return;               // bounded; later marks are dropped
+    if (h->ev_used == h->ev_pool.size()) {
+        cudaEvent_t e;
+        if (cudaEventCreate(&e) != cudaSuccess) return;
+        h->ev_pool.push_back(e);
+    }
+    cudaEvent_t e = h->ev_pool[h->ev_used++];
+    cudaEventRecord(e, st);
+    h->ev_marks.emplace_back(slot, e);
+}
+
+int profile_collect(svx_handle* h) {
+    if (h->ev_marks.empty()) return 0;
+    SVX_CUDA_CHECK(cudaEventSynchronize(h->ev_marks.back().second));
+    for (size_t i = 0; i + 1 < h->ev_marks.size(); ++i) {
+        const int slot = h->ev_marks[i].first;
+        if (slot < 0) continue;
+        float ms = 0.f;
+        SVX_CUDA_CHECK(cudaEventElapsedTime(&ms, h->ev_marks[i].second, h->ev_marks[i + 1].second));
+        h->prof_ms[slot] += ms;
+        h->prof_launches[slot] += 1;
+    }
+    h->ev_marks.clear();
+    h->ev_used = 0;
+    return 0;
+}
+
+// x1 (conv1 operand) of `n` sites is resident -> labels / probs / logits
+int run_cnn(svx_handle* h, long long n, int32_t* labels, float* probs, float* logits,
+            cudaStream_t st) {
+    int rc;
+    const long long rows[L_COUNT] = {n * P1, n * P2, n * P3, n * P3, n * P3, n, n};
+    for (int li = 0; li < L_COUNT; ++li) h->layer[li].m_rows = rows[li];
+
+    mark(h, 1, st);
+    if ((rc = launch_gemm_layer(h->layer[L_CONV1], h->num_sms, st))) return rc;
+    PoolParams p1{};
+    p1.in = h->y1; p1.in_grid_w = S2D; p1.in_pos_per_img = P1; p1.C = 96; p1.out_h = 27; p1.out_w = 27;
+    p1.lrn = 1; p1.out_hi = h->x2_hi; p1.out_lo = h->x2_lo; p1.out_ld = 128; p1.out_grid_w = G2;
+    p1.out_pos_per_img = P2; p1.group_real = 48; p1.group_pad = 64; p1.flatten = 0;
+    mark(h, 2, st);
+    if ((rc = launch_pool(p1, n, h->num_sms, st))) return rc;
+
+    mark(h, 3, st);
+    if ((rc = launch_gemm_layer(h->layer[L_CONV2], h->num_sms, st))) return rc;
+    PoolParams p2{};
+    p2.in = h->y2; p2.in_grid_w = G2; p2.in_pos_per_img = P2; p2.C = 256; p2.out_h = 13; p2.out_w = 13;
+    p2.lrn = 1; p2.out_hi = h->x3_hi; p2.out_lo = h->x3_lo; p2.out_ld = 256; p2.out_grid_w = G3;
+    p2.out_pos_per_img = P3; p2.group_real = 256; p2.group_pad = 256; p2.flatten = 0;
+    mark(h, 4, st);
+    if ((rc = launch_pool(p2, n, h->num_sms, st))) return rc;
+
+    mark(h, 5, st);
+    if ((rc = launch_gemm_layer(h->layer[L_CONV3], h->num_sms, st))) return rc;
+    mark(h, 6, st);
+    if ((rc = launch_gemm_layer(h->layer[L_CONV4], h->num_sms, st))) return rc;
+    mark(h, 7, st);
+    if ((rc = launch_gemm_layer(h->layer[L_CONV5], h->num_sms, st))) return rc;
+    PoolParams p5{};
+    p5.in = h->y5; p5.in_grid_w = G3; p5.in_pos_per_img = P3; p5.C = 256; p5.out_h = 6; p5.out_w = 6;
+    p5.lrn = 0; p5.out_hi = h->x6_hi; p5.out_lo = h->x6_lo; p5.out_ld = 9216; p5.out_grid_w = 6;
+    p5.out_pos_per_img = 36; p5.group_real = 256; p5.group_pad = 256; p5.flatten = 1;
+    mark(h, 8, st);
+    if ((rc = launch_pool(p5, n, h->num_sms, st))) return rc;
+
+    mark(h, 9, st);
+    if ((rc = launch_gemm_layer(h->layer[L_FC6], h->num_sms, st))) return rc;
+    mark(h, 10, st);
+    if ((rc = launch_gemm_layer(h->layer[L_FC7], h->num_sms, st))) return rc;
+    mark(h, 11, st);
+    if ((rc = launch_fc8_softmax(h->x8_hi, h->x8_lo, h->w8, h->b8, n, labels, probs, logits, st))) return rc;
+    mark(h, -1, st);
+    h->last_n = n;
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* svx_last_error(void) { return g_error.c_str(); }
+const char* svx_version(void) { return "svx 0.1 (sm_100a; tcgen05+TMA)"; }
+int64_t svx_launch_count(void) { return g_launches; }
+void svx_launch_count_reset(void) { g_launches = 0; }
+int64_t svx_max_batch(const svx_handle* h) { return h ? h->max_batch : 0; }
+int svx_device(const svx_handle* h) { return h ? h->device : -1; }
+
+int svx_create(const svx_weights* weights, int device, int64_t max_batch, int precision,
+               svx_handle** out) {
+    if (!out) return fail(SVX_ERR_INVALID, "svx_create: out is NULL");
+    *out = nullptr;
+    if (max_batch <= 0 || max_batch > (1 << 20)) return fail(SVX_ERR_INVALID, "svx_create: bad max_batch");
+    if (precision != SVX_PRECISION_3PASS && precision != SVX_PRECISION_1PASS)
+        return fail(SVX_ERR_INVALID, "svx_create: bad precision");
+    int ndev = 0;
+    SVX_CUDA_CHECK(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) return fail(SVX_ERR_INVALID, "svx_create: no such device");
+    DeviceGuard guard(device);
+    if (!guard.ok) return fail(SVX_ERR_CUDA, "svx_create: cannot select device");
+    cudaDeviceProp prop;
+    SVX_CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+        return fail(SVX_ERR_UNSUPPORTED, std::string("svx_create: device '") + prop.name +
+                                             "' is not sm_100 (this library has no other code path)");
+    std::unique_ptr<svx_handle> h(new svx_handle());
+    h->device = device;
+    h->num_sms = prop.multiProcessorCount;
+    h->max_batch = max_batch;
+    h->precision = precision;
+    auto cleanup = [&](int rc) {
+        for (void* p : h->allocs) cudaFree(p);
+        if (h->stream) cudaStreamDestroy(h->stream);
+        return rc;
+    };
+    int rc;
+    SVX_CUDA_CHECK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    if ((rc = dev_alloc(h.get(), &h->rows_dev, (size_t)max_batch * SVX_ROW_FIELDS))) return cleanup(rc);
+    if ((rc = dev_alloc(h.get(), &h->labels_dev, (size_t)max_batch))) return cleanup(rc);
+    if ((rc = dev_alloc(h.get(), &h->probs_dev, (size_t)max_batch * SVX_NUM_CLASSES))) return cleanup(rc);
+    if (weights) {
+        if ((rc = dev_alloc(h.get(), &h->x1, (size_t)max_batch * P1 * 64))) return cleanup(rc);
+        if ((rc = build_model(h.get(), weights))) return cleanup(rc);
+    }
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) return cleanup(fail(SVX_ERR_CUDA, std::string("svx_create: ") + cudaGetErrorString(e)));
+    *out = h.release();
+    return SVX_OK;
+}
+
+void svx_destroy(svx_handle* h) {
+    if (!h) return;
+    DeviceGuard guard(h->device);
+    cudaDeviceSynchronize();
+    for (void* p : h->allocs) cudaFree(p);
+    for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+int svx_set_profiling(svx_handle* h, int enable) {
+    if (!h) return fail(SVX_ERR_INVALID, "svx_set_profiling: NULL handle");
+    DeviceGuard guard(h->device);
+    int rc = profile_collect(h);
+    h->profiling = enable != 0;
+    return rc;
+}
+
+int svx_profile_read(svx_handle* h, float* ms_out, int64_t* launches_out, int reset) {
+    if (!h) return fail(SVX_ERR_INVALID, "svx_profile_read: NULL handle");
+    DeviceGuard guard(h->device);
+    int rc = profile_collect(h);
+    if (rc) return rc;
+    for (int i = 0; i < SVX_PROFILE_SLOTS; ++i) {
+        if (ms_out) ms_out[i] = (float)h->prof_ms[i];
+        if (launches_out) launches_out[i] = h->prof_launches[i];
+        if (reset) { h->prof_ms[i] = 0.0; h->prof_launches[i] = 0; }
+    }
+    return SVX_OK;
+}
+
+int svx_encode(svx_handle* h, const int32_t* rows_dev, int64_t n, void* images_dev, int dtype,
+               void* stream) {
+    if (!h) return fail(SVX_ERR_INVALID, "svx_encode: NULL handle");
+    if (n < 0 || (n > 0 && (!rows_dev || !images_dev))) return fail(SVX_ERR_INVALID, "svx_encode: bad arguments");
+    if (dtype != SVX_IMAGE_F32 && dtype != SVX_IMAGE_F16) return fail(SVX_ERR_INVALID, "svx_encode: bad dtype");
+    if (reinterpret_cast<uintptr_t>(images_dev) & 15) return fail(SVX_ERR_INVALID, "svx_encode: images_dev must be 16-byte aligned");
+    DeviceGuard guard(h->device);
+    return launch_encode(rows_dev, n, images_dev, dtype == SVX_IMAGE_F32 ? 0 : 1, h->num_sms,
+                         static_cast<cudaStream_t>(stream));
+}
+
+int svx_forward(svx_handle* h, const void* images_dev, int dtype, int64_t n, float* logits_dev,
+                void* stream) {
+    if (!h || !h->has_model) return fail(SVX_ERR_INVALID, "svx_forward: handle has no model");
+    if (n < 0 || (n > 0 && (!images_dev || !logits_dev))) return fail(SVX_ERR_INVALID, "svx_forward: bad arguments");
+    if (dtype != SVX_IMAGE_F32 && dtype != SVX_IMAGE_F16) return fail(SVX_ERR_INVALID, "svx_forward: bad dtype");
+    DeviceGuard guard(h->device);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const size_t esz = dtype == SVX_IMAGE_F32 ? 4 : 2;
+    for (int64_t s = 0; s < n; s += h->max_batch) {
+        const int64_t m = n - s < h->max_batch ? n - s : h->max_batch;
+        const char* src = static_cast<const char*>(images_dev) + (size_t)s * SVX_IMG * SVX_IMG * 3 * esz;
+        int rc;
+        if ((rc = launch_nhwc_to_s2d(src, dtype, m, h->x1, st))) return rc;
+        if ((rc = run_cnn(h, m, h->labels_dev, h->probs_dev, logits_dev + s * SVX_NUM_CLASSES, st))) return rc;
+    }
+    return SVX_OK;
+}
+
+int svx_classify_device(svx_handle* h, const int32_t* rows_dev, int64_t n, int32_t* labels_dev,
+                        float* probs_dev, float* logits_dev, void* stream) {
+    if (!h || !h->has_model) return fail(SVX_ERR_INVALID, "svx_classify_device: handle has no model");
+    if (n < 0 || (n > 0 && (!rows_dev || !labels_dev || !probs_dev)))
+        return fail(SVX_ERR_INVALID, "svx_classify_device: bad arguments");
+    DeviceGuard guard(h->device);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    for (int64_t s = 0; s < n; s += h->max_batch) {
+        const int64_t m = n - s < h->max_batch ? n - s : h->max_batch;
+        int rc;
+        mark(h, 0, st);
+        if ((rc = launch_encode(rows_dev + s * SVX_ROW_FIELDS, m, h->x1, 2, h->num_sms, st))) return rc;
+        if ((rc = run_cnn(h, m, labels_dev + s, probs_dev + s * SVX_NUM_CLASSES,
+                          logits_dev ? logits_dev + s * SVX_NUM_CLASSES : nullptr, st)))
+            return rc;
+    }
+    return SVX_OK;
+}
+
+int svx_classify(svx_handle* h, const int32_t* rows_host, int64_t n, int32_t* labels_host,
+                 float* probs_host) {
+    if (!h || !h->has_model) return fail(SVX_ERR_INVALID, "svx_classify: handle has no model");
+    if (n < 0 || (n > 0 && (!rows_host || !labels_host || !probs_host)))
+        return fail(SVX_ERR_INVALID, "svx_classify: bad arguments");
+    DeviceGuard guard(h->device);
+    cudaStream_t st = h->stream;
+    for (int64_t s = 0; s < n; s += h->max_batch) {
+        const int64_t m = n - s < h->max_batch ? n - s : h->max_batch;
+        int rc;
+        SVX_CUDA_CHECK(cudaMemcpyAsync(h->rows_dev, rows_host + s * SVX_ROW_FIELDS,
+                                       (size_t)m * SVX_ROW_FIELDS * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+        mark(h, 0, st);
+        if ((rc = launch_encode(h->rows_dev, m, h->x1, 2, h->num_sms, st))) return rc;
+        if ((rc = run_cnn(h, m, h->labels_dev, h->probs_dev, nullptr, st))) return rc;
+        SVX_CUDA_CHECK(cudaMemcpyAsync(labels_host + s, h->labels_dev, (size_t)m * sizeof(int32_t),
+                                       cudaMemcpyDeviceToHost, st));
+        SVX_CUDA_CHECK(cudaMemcpyAsync(probs_host + s * SVX_NUM_CLASSES, h->probs_dev,
+                                       (size_t)m * SVX_NUM_CLASSES * sizeof(float), cudaMemcpyDeviceToHost, st));
+    }
+    SVX_CUDA_CHECK(cudaStreamSynchronize(st));
+    return SVX_OK;
+}
+
+int svx_debug_activation(svx_handle* h, const char* name, int64_t n, float* out_host) {
+    if (!h || !h->has_model || !name || !out_host) return fail(SVX_ERR_INVALID, "svx_debug_activation: bad arguments");
+    if (n <= 0 || n > h->last_n) return fail(SVX_ERR_INVALID, "svx_debug_activation: n exceeds the last micro-batch");
+    DeviceGuard guard(h->device);
+    SVX_CUDA_CHECK(cudaDeviceSynchronize());
+    struct Src { const char* name; const float* f32; const __half* hi; const __half* lo; int pos, grid_w, H, W, ld, C, greal, gpad; };
+    const Src table[] = {
+        {"conv1", h->y1, nullptr, nullptr, P1, S2D, 55, 55, 96, 96, 96, 96},
+        {"norm1", nullptr, h->x2_hi, h->x2_lo, P2, G2, 27, 27, 128, 96, 48, 64},
+        {"conv2", h->y2, nullptr, nullptr, P2, G2, 27, 27, 256, 256, 256, 256},
+        {"norm2", nullptr, h->x3_hi, h->x3_lo, P3, G3, 13, 13, 256, 256, 256, 256},
+        {"conv3", nullptr, h->x4_hi, h->x4_lo, P3, G3, 13, 13, 384, 384, 384, 384},
+        {"conv4", nullptr, h->x5_hi, h->x5_lo, P3, G3, 13, 13, 384, 384, 384, 384},
+        {"conv5", h->y5, nullptr, nullptr, P3, G3, 13, 13, 256, 256, 256, 256},
+        {"pool5", nullptr, h->x6_hi, h->x6_lo, 36, 6, 6, 6, 256, 256, 256, 256},
+        {"fc6", nullptr, h->x7_hi, h->x7_lo, 1, 1, 1, 1, 4096, 4096, 4096, 4096},
+        {"fc7", nullptr, h->x8_hi, h->x8_lo, 1, 1, 1, 1, 4096, 4096, 4096, 4096},
+    };
+    for (const Src& s : table) {
+        if (std::strcmp(s.name, name) != 0) continue;
+        const size_t count = (size_t)n * s.pos * s.ld;
+        std::vector<float> buf(count);
+        if (s.f32) {
+            SVX_CUDA_CHECK(cudaMemcpy(buf.data(), s.f32, count * sizeof(float), cudaMemcpyDeviceToHost));
+        } else {
+            std::vector<__half> hi(count), lo(count);
+            SVX_CUDA_CHECK(cudaMemcpy(hi.data(), s.hi, count * sizeof(__half), cudaMemcpyDeviceToHost));
+            SVX_CUDA_CHECK(cudaMemcpy(lo.data(), s.lo, count * sizeof(__half), cudaMemcpyDeviceToHost));
+            for (size_t i = 0; i < count; ++i) buf[i] = __half2float(hi[i]) + __half2float(lo[i]);
+        }
+        size_t o = 0;
+        for (int64_t im = 0; im < n; ++im)
+            for (int y = 0; y < s.H; ++y)
+                for (int x = 0; x < s.W; ++x)
+                    for (int c = 0; c < s.C; ++c) {
+                        const int col = (c / s.greal) * s.gpad + (c % s.greal);
+                        out_host[o++] = buf[((size_t)im * s.pos + (size_t)y * s.grid_w + x) * s.ld + col];
+                    }
+        return SVX_OK;
+    }
+    return fail(SVX_ERR_INVALID, std::string("svx_debug_activation: unknown activation '") + name + "'");
+}
+
+int svx_gemm_selftest(int device, const float* a_dev, const float* b_dev, float* c_dev, int64_t m,
+                      int64_t n, int64_t k, int block_n, int precision, void* stream) {
+    if (!a_dev || !b_dev || !c_dev || m <= 0 || n <= 0 || k <= 0)
+        return fail(SVX_ERR_INVALID, "svx_gemm_selftest: bad arguments");
+    if (k % GEMM_BLOCK_K != 0 || n % block_n != 0)
+        return fail(SVX_ERR_INVALID, "svx_gemm_selftest: k must be a multiple of 64 and n of block_n");
+    DeviceGuard guard(device);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    cudaDeviceProp prop;
+    SVX_CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) return fail(SVX_ERR_UNSUPPORTED, "svx_gemm_selftest: device is not sm_100");
+    __half *a_hi = nullptr, *a_lo = nullptr, *b_hi = nullptr, *b_lo = nullptr;
+    float* bias = nullptr;
+    auto free_all = [&](int rc) {
+        cudaStreamSynchronize(st);
+        cudaFree(a_hi); cudaFree(a_lo); cudaFree(b_hi); cudaFree(b_lo); cudaFree(bias);
+        return rc;
+    };
+    SVX_CUDA_CHECK(cudaMalloc(&a_hi, (size_t)m * k * 2));
+    SVX_CUDA_CHECK(cudaMalloc(&a_lo, (size_t)m * k * 2));
+    SVX_CUDA_CHECK(cudaMalloc(&b_hi, (size_t)n * k * 2));
+    SVX_CUDA_CHECK(cudaMalloc(&b_lo, (size_t)n * k * 2));
+    SVX_CUDA_CHECK(cudaMalloc(&bias, (size_t)n * 4));
+    SVX_CUDA_CHECK(cudaMemsetAsync(bias, 0, (size_t)n * 4, st));
+    int rc;
+    if ((rc = launch_split_hilo(a_dev, m * k, a_hi, a_lo, st))) return free_all(rc);
+    if ((rc = launch_split_hilo(b_dev, n * k, b_hi, b_lo, st))) return free_all(rc);
+    GemmLayer L;
+    std::memset(&L, 0, sizeof(L));
+    if ((rc = make_tensor_map_2d(&L.tm_a_hi, a_hi, m, k, k, GEMM_BLOCK_M))) return free_all(rc);
+    if ((rc = make_tensor_map_2d(&L.tm_a_lo, a_lo, m, k, k, GEMM_BLOCK_M))) return free_all(rc);
+    if ((rc = make_tensor_map_2d(&L.tm_b_hi, b_hi, n, k, k, block_n))) return free_all(rc);
+    if ((rc = make_tensor_map_2d(&L.tm_b_lo, b_lo, n, k, k, block_n))) return free_all(rc);
+    L.block_n = block_n; L.chunk_kblocks = kChunkKBlocks; L.groups = 1; L.n_per_group = (int)n; L.taps = 1; L.cblocks = (int)(k / GEMM_BLOCK_K);
+    L.a_group_cols = 0; L.row_off[0] = 0;
+    L.use_a_lo = L.use_b_lo = precision == SVX_PRECISION_3PASS ? 1 : 0;
+    L.m_rows = m; L.bias = bias; L.relu = 0; L.out_f32 = c_dev; L.ldc = (int)n;
+    rc = launch_gemm_layer(L, prop.multiProcessorCount, st);
+    return free_all(rc);
+}
+
+}  // extern "C"

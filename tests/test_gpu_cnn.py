@@ -1,0 +1,96 @@
+"""GPU parity: tcgen05 layer kernel and the full encode+classify path against the oracle.
+Tolerances are the north-star's: labels identical, softmax within 1e-3 (fp32)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import alexnet, encoder_c
+from svision_b200 import classifier as C, sites
+
+pytestmark = pytest.mark.gpu
+
+SOFTMAX_TOL = 1e-3          # BASELINE.json north_star
+LOGIT_TOL = 4e-3            # |dsoftmax| <= 1e-3  =>  |dlogit| <~ 4e-3
+
+
+@pytest.mark.parametrize("m,n,k,bn", [(128, 128, 64, 128), (1000, 256, 512, 128), (300, 96, 192, 96),
+                                      (700, 384, 320, 64), (513, 512, 1024, 128), (2048, 1024, 9216, 128)])
+def test_gemm_kernel_3pass(m, n, k, bn):
+    torch.manual_seed(m + n + k)
+    a = torch.randn(m, k, device="cuda")
+    b = torch.randn(n, k, device="cuda") * 0.05
+    ref = a.double() @ b.double().T
+    c = C.gemm_selftest(a, b, block_n=bn, precision="3pass")
+    # hi/lo split carries ~22 bits; fp32 accumulation over k terms
+    assert (c.double() - ref).abs().max().item() < 2e-5 * ref.abs().max().item() + 1e-5
+    c1 = C.gemm_selftest(a, b, block_n=bn, precision="1pass")
+    assert (c1.double() - ref).abs().max().item() < 2e-2 * ref.abs().max().item()
+
+
+@pytest.fixture(scope="module")
+def clf(synthetic_weights):
+    c = C.Classifier(synthetic_weights, device=0, max_batch=64)
+    yield c
+    c.close()
+
+
+def test_layerwise_activations_match_oracle(clf, cnn_golden, synthetic_weights):
+    rows = cnn_golden["rows"][:16]
+    imgs = encoder_c.encode_f32(rows)
+    _, inter = alexnet.forward(imgs, synthetic_weights, torch.float32, return_intermediates=True)
+    clf.classify_device(clf.rows_to_device(rows))
+    torch.cuda.synchronize()
+    for name in ("conv1", "norm1", "conv2", "norm2", "conv3", "conv4", "conv5", "pool5", "fc6", "fc7"):
+        got = clf.debug_activation(name, rows.shape[0])
+        ref = inter[name].numpy()
+        scale = np.abs(ref).max()
+        assert np.abs(got - ref).max() < 2e-4 * scale + 1e-5, name
+
+
+def test_labels_and_softmax_match_oracle(clf, cnn_golden):
+    rows = cnn_golden["rows"]
+    ref_logits = torch.from_numpy(cnn_golden["logits_fp64"])
+    labels, probs, logits = clf.classify_device(clf.rows_to_device(rows), want_logits=True)
+    assert (logits.cpu().double() - ref_logits).abs().max().item() < LOGIT_TOL
+    assert (probs.cpu().double() - torch.softmax(ref_logits, 1)).abs().max().item() < SOFTMAX_TOL
+    assert np.array_equal(labels.cpu().numpy(), ref_logits.argmax(1).numpy().astype(np.int32))
+
+
+def test_host_entry_equals_device_entry_and_ragged_batches(clf, cnn_golden):
+    # 256 rows through max_batch=64 -> 4 micro-batches; 77 rows -> ragged tail
+    rows = cnn_golden["rows"]
+    l_dev, p_dev = clf.classify_device(clf.rows_to_device(rows))
+    l_host, p_host = clf.classify(rows)
+    assert l_host.dtype == np.int32 and p_host.dtype == np.float32
+    assert np.array_equal(l_host, l_dev.cpu().numpy())
+    assert np.array_equal(p_host, p_dev.cpu().numpy())
+    l77, p77 = clf.classify(rows[:77])
+    assert np.array_equal(l77, l_host[:77]) and np.array_equal(p77, p_host[:77])
+    l0, p0 = clf.classify(np.zeros((0, 12), np.int32))
+    assert l0.shape == (0,) and p0.shape == (0, 5)
+
+
+def test_forward_on_encoder_images_equals_fused_path(clf, cnn_golden):
+    rows = cnn_golden["rows"][:48]
+    rd = clf.rows_to_device(rows)
+    _, _, logits = clf.classify_device(rd, want_logits=True)
+    for dt in (torch.float16, torch.float32):
+        l2 = clf.forward(clf.encode(rd, dtype=dt))
+        assert torch.equal(l2, logits)
+
+
+def test_results_independent_of_batch_position(clf, cnn_golden):
+    # sites are independent: permuting the batch permutes the results bit-for-bit
+    rows = cnn_golden["rows"][:64]
+    perm = np.random.default_rng(0).permutation(64)
+    l1, p1 = clf.classify(rows)
+    l2, p2 = clf.classify(rows[perm])
+    assert np.array_equal(l1[perm], l2) and np.array_equal(p1[perm], p2)
+
+
+def test_softmax_rows_sum_to_one_full_size(clf):
+    rows = sites.make_sites_p1(2000, seed=sites.SEED_CONFIG2)
+    labels, probs = clf.classify(rows)
+    assert np.abs(probs.sum(1) - 1).max() < 1e-5
+    assert ((labels >= 0) & (labels < 5)).all()
+    assert np.array_equal(labels, probs.argmax(1).astype(np.int32))

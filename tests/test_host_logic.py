@@ -1,0 +1,137 @@
+"""CPU: host-side logic around the kernels -- BED parsing, per-row replay, sharding + all-gather
+(world_size 2 over gloo)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from svision_b200 import bed, predict, sharded, sites
+
+
+def _write_bed(tmp_path, rows, extra=None):
+    lines = sites.rows_to_bed_lines(rows, region_size=5)
+    if extra:
+        lines += extra
+    p = tmp_path / "chr1.segments.all.bed"
+    p.write_text("\n".join(lines) + "\n")
+    return str(p)
+
+
+def test_bed_roundtrip(tmp_path):
+    rows = np.concatenate([sites.edge_case_sites(), sites.make_sites_p2(200, seed=4)])
+    t = bed.read_segments_bed(_write_bed(tmp_path, rows))
+    assert t.rows.dtype == np.int32 and np.array_equal(t.rows, rows)
+    assert len(t) == rows.shape[0]
+    # label string layout of create_batch.py:48: col13, col0, col15..col22 joined by 'svision'
+    lab = t.label_strings()[7].split("svision")
+    assert lab[0] == "2m" and lab[1].startswith("chr1+1000+") and lab[2] == "read7" and len(lab) == 10
+
+
+def test_bed_invalid_strand_token_takes_reverse_branch(tmp_path):
+    line = sites.rows_to_bed_lines(sites.make_sites_p1(1, seed=1))[0].split("\t")
+    line[5] = "None"          # neither 'True' nor 'False' -> forward=None -> falsy (create_batch.py:115)
+    line[10] = "true"         # case matters in the reference
+    t = bed.read_segments_bed(_write_bed(tmp_path, np.zeros((0, 12), np.int32), ["\t".join(line)]))
+    assert t.rows[0, 4] == 0 and t.rows[0, 9] == 0
+
+
+def test_bed_empty_and_malformed(tmp_path):
+    p = tmp_path / "e.bed"
+    p.write_text("")
+    assert len(bed.read_segments_bed(str(p))) == 0
+    p.write_text("a\tb\tc\n")
+    with pytest.raises(ValueError):
+        bed.read_segments_bed(str(p))
+
+
+def test_replay_rows_region_flush_and_rules(tmp_path):
+    rows = sites.make_sites_p1(12, seed=2)
+    lines = [l.split("\t") for l in sites.rows_to_bed_lines(rows, region_size=4)]
+    lines[1][13] = "1"        # a main x minor pair (no 'm'): INS/DEL predictions are ignored
+    lines[2][20] = "True"     # forward signature predicted INV -> dropped entirely
+    t = bed.read_segments_bed(_write_bed(tmp_path, np.zeros((0, 12), np.int32),
+                                         ["\t".join(l) for l in lines]))
+    labels = np.array([1, 0, 2, 3, 1, 1, 1, 1, 4, 4, 4, 4], dtype=np.int32)
+    probs = np.full((12, 5), 0.05, dtype=np.float32)
+    probs[np.arange(12), labels] = 0.8
+    seen = []
+    n = predict.replay_rows(t, labels, probs, lambda *a: seen.append(a))
+    assert n == 3 and [s[0] for s in seen] == ["chr1+0+500+4", "chr1+1000+1500+4", "chr1+2000+2500+4"]
+    region0 = seen[0]
+    assert region0[1] == {"0": {1: [100, 200, 100]}, "3": {3: [100, 200, 100]}}   # rows 0 and 3 only
+    assert len(region0[5]) == 3 and all(isinstance(s, np.float32) for s in region0[5])
+    assert region0[5][0] == np.float32(0.8)
+    assert set(region0[2]) == {"0", "1", "3"}                                   # row 2 was dropped
+
+
+def test_run_predict_writes_reference_files(tmp_path):
+    rows = sites.make_sites_p1(9, seed=3)
+    path = _write_bed(tmp_path, rows)
+
+    class FakeClf:
+        def classify(self, r):
+            p = np.full((r.shape[0], 5), 0.1, dtype=np.float32)
+            p[:, 1] = 0.6
+            return np.ones(r.shape[0], dtype=np.int32), p
+
+    calls = []
+
+    def write(vcf, score, stats, region, *rest):
+        calls.append(region)
+        vcf.write(region + "\n")
+
+    class Opt:
+        model_path = "unused"
+    n = predict.run_predict(path, str(tmp_path / "chr1.predict.s5"), Opt(), lambda d: sorted(d), write,
+                            classifier=FakeClf(), chrom="chr1")
+    assert n == 2 and calls == ["chr1+0+500+5", "chr1+1000+1500+5"]
+    assert (tmp_path / "chr1.predict.s5.vcf").read_text().count("\n") == 2
+    assert (tmp_path / "chr1.predict.s5.score.txt").exists()
+
+
+def test_shard_bounds_cover_everything():
+    for n in (0, 1, 7, 8, 9, 100_000):
+        for world in (1, 2, 3, 8):
+            got = []
+            for r in range(world):
+                a, b, per = sharded.shard_bounds(n, world, r)
+                assert b - a <= per
+                got += list(range(a, b))
+                assert sharded.shard_rows(np.zeros((n, 12), np.int32), world, r).shape == (per, 12)
+            assert got == list(range(n))
+
+
+def _fake_classify(rows):
+    labels = (np.abs(rows[:, 5].astype(np.int64)) % 5).astype(np.int32)
+    probs = np.zeros((rows.shape[0], 5), dtype=np.float32)
+    probs[np.arange(rows.shape[0]), labels] = 0.5 + (rows[:, 10] % 97) / 200.0
+    return labels, probs
+
+
+def _worker(rank, world, port, n, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    rows = sites.make_sites_p1(n, seed=9)
+    labels, probs = sharded.classify_sharded(_fake_classify, rows)
+    ref_l, ref_p = _fake_classify(rows)
+    q.put((rank, bool(np.array_equal(labels, ref_l)), bool(np.array_equal(probs, ref_p))))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n", [101, 64])
+def test_sharded_all_gather_gloo_world2(n):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 500) + n
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, n, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+    assert res == [(0, True, True), (1, True, True)]
