@@ -114,6 +114,19 @@ int svx_debug_activation(svx_handle *h, const char *name, int64_t n, float *out_
 int svx_gemm_selftest(int device, const float *a_dev, const float *b_dev, float *c_dev,
                       int64_t m, int64_t n, int64_t k, int block_n, int precision, void *stream);
 
+/* Shifted-GEMM self-test: C[m][n] = sum_t sum_c A[m + row_off[t]][c] * B[n][t*k_per_tap + c]
+ * (rows outside A read as zero).  flags bit0: slab kernel (conv_tc.cu) instead of the per-tap
+ * kernel (gemm_tc.cu); bit1: descriptor base_offset mode for row-shifted slab views. */
+int svx_conv_selftest(int device, const float *a_dev, const float *b_dev, float *c_dev, int64_t m,
+                      int64_t n, int64_t k_per_tap, int taps, const int *row_off, int block_n,
+                      int precision, int flags, void *stream);
+
+/* Development aid: per-role cycle counters of the 7 tensor-core layers, uint64 out[7][8]
+ * (handle created with SVX_DBG=1 in the environment): 0 MMA-role total, 1 MMA wait operands,
+ * 2 MMA wait TMEM-empty, 3 k-blocks, 4 producer wait smem-empty, 5 epilogue wait TMEM-full,
+ * 6 epilogue drain, 7 epilogue store; summed over CTAs. */
+int svx_debug_counters(svx_handle *h, uint64_t *out, int reset);
+
 /* Per-kernel device timing with CUDA events recorded on the launching stream (bench.py's live
  * roofline numbers).  Slots: 0 encode, 1 conv1, 2 pool1+lrn1, 3 conv2, 4 pool2+lrn2, 5 conv3,
  * 6 conv4, 7 conv5, 8 pool5, 9 fc6, 10 fc7, 11 fc8+softmax.  svx_profile_read synchronises,

@@ -14,7 +14,7 @@ PRECISION_3PASS, PRECISION_1PASS = 0, 1
 #: every symbol include/svx.h declares (tests check the .so exports exactly these)
 SYMBOLS = (
     "svx_create", "svx_destroy", "svx_encode", "svx_forward", "svx_classify_device",
-    "svx_classify", "svx_debug_activation", "svx_gemm_selftest", "svx_set_profiling",
+    "svx_classify", "svx_debug_activation", "svx_gemm_selftest", "svx_conv_selftest", "svx_debug_counters", "svx_set_profiling",
     "svx_profile_read", "svx_launch_count",
     "svx_launch_count_reset", "svx_max_batch", "svx_device", "svx_last_error", "svx_version",
 )
@@ -58,6 +58,10 @@ def load() -> ctypes.CDLL:
     lib.svx_debug_activation.restype = i32
     lib.svx_gemm_selftest.argtypes = [i32, vp, vp, vp, i64, i64, i64, i32, i32, vp]
     lib.svx_gemm_selftest.restype = i32
+    lib.svx_conv_selftest.argtypes = [i32, vp, vp, vp, i64, i64, i64, i32, vp, i32, i32, i32, vp]
+    lib.svx_conv_selftest.restype = i32
+    lib.svx_debug_counters.argtypes = [vp, vp, i32]
+    lib.svx_debug_counters.restype = i32
     lib.svx_set_profiling.argtypes = [vp, i32]
     lib.svx_set_profiling.restype = i32
     lib.svx_profile_read.argtypes = [vp, vp, vp, i32]

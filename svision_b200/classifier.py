@@ -165,6 +165,13 @@ class Classifier:
                    "svx_profile_read")
         return {k: (float(m), int(c)) for k, m, c in zip(self.PROFILE_SLOTS, ms, cnt)}
 
+    def debug_counters(self, reset: bool = True) -> np.ndarray:
+        """uint64[7,8] per-role cycle counters (handle must be created with SVX_DBG=1)."""
+        out = np.zeros((7, 8), dtype=np.uint64)
+        _lib.check(self._lib.svx_debug_counters(self._h, out.ctypes.data, int(reset)),
+                   "svx_debug_counters")
+        return out
+
     def debug_activation(self, name: str, n: int) -> np.ndarray:
         shapes = {"conv1": (55, 55, 96), "norm1": (27, 27, 96), "conv2": (27, 27, 256),
                   "norm2": (13, 13, 256), "conv3": (13, 13, 384), "conv4": (13, 13, 384),
@@ -189,6 +196,26 @@ def gemm_selftest(a: torch.Tensor, b: torch.Tensor, block_n: int = 128,
                                      m, n, k, block_n, prec,
                                      torch.cuda.current_stream(a.device).cuda_stream),
                "svx_gemm_selftest")
+    return c
+
+
+def conv_selftest(a: torch.Tensor, b: torch.Tensor, row_off, block_n: int = 128,
+                  precision: str = "3pass", slab: bool = True, base_offset_mode: int = 1) -> torch.Tensor:
+    """C[m,n] = sum_t A[m + row_off[t], :] @ B[n, t*K:(t+1)*K].T through a tensor-core layer kernel
+    (A [M,K], B [N,taps*K] float32 cuda tensors; rows outside A read as zero)."""
+    lib = _lib.load()
+    a, b = a.contiguous(), b.contiguous()
+    m, k = a.shape
+    n = b.shape[0]
+    offs = np.ascontiguousarray(row_off, dtype=np.int32)
+    assert b.shape[1] == k * offs.size
+    c = torch.empty((m, n), dtype=torch.float32, device=a.device)
+    prec = {"3pass": _lib.PRECISION_3PASS, "1pass": _lib.PRECISION_1PASS}[precision]
+    flags = (1 if slab else 0) | ((base_offset_mode & 1) << 1)
+    _lib.check(lib.svx_conv_selftest(a.device.index or 0, a.data_ptr(), b.data_ptr(), c.data_ptr(),
+                                     m, n, k, int(offs.size), offs.ctypes.data, block_n, prec, flags,
+                                     torch.cuda.current_stream(a.device).cuda_stream),
+               "svx_conv_selftest")
     return c
 
 

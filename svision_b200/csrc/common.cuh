@@ -74,6 +74,19 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     }
 }
 
+// Warp-uniform election of exactly one lane (elect.sync): code under `if (elect_one())` may use
+// uniform-datapath instructions (UTCHMMA, UTMALDG, UTCBAR) without a per-thread serialisation loop.
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred = 0;
+    asm volatile(
+        "{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\t"
+        "elect.sync rx|px, %1;\n\t"
+        "selp.b32 %0, 1, 0, px;\n\t}"
+        : "=r"(pred)
+        : "r"(0xffffffffu));
+    return pred != 0;
+}
+
 __device__ __forceinline__ void fence_proxy_async_smem() {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }

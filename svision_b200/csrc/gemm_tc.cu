@@ -108,6 +108,7 @@ gemm_tc_kernel(const __grid_constant__ GemmLayer L) {
                                       C::B_TILE_BYTES * (1 + (L.use_b_lo ? 1 : 0));
             int stage = 0;
             uint32_t phase = 0;
+            long long c_prod_wait = 0;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
                 const int g = tile / tiles_per_group;
                 const int rem = tile - g * tiles_per_group;
@@ -120,7 +121,7 @@ gemm_tc_kernel(const __grid_constant__ GemmLayer L) {
                 for (int t = 0; t < L.taps; ++t) {
                     const int a_row = m0 + L.row_off[t];
                     for (int cb = 0; cb < L.cblocks; ++cb, ++kb) {
-                        mbar_wait(&empty_bar[stage], phase ^ 1u);
+                        { const long long t0 = clock64(); mbar_wait(&empty_bar[stage], phase ^ 1u); c_prod_wait += clock64() - t0; }
                         uint8_t* st = smem + stage * C::STAGE_BYTES;
                         mbar_arrive_expect_tx(&full_bar[stage], stage_tx);
                         tma_load_2d(&L.tm_a_hi, &full_bar[stage], st, a_col0 + cb * BLOCK_K, a_row);
@@ -136,6 +137,7 @@ gemm_tc_kernel(const __grid_constant__ GemmLayer L) {
                     }
                 }
             }
+            if (L.dbg) atomicAdd(&L.dbg[4], (unsigned long long)c_prod_wait);
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
@@ -146,14 +148,16 @@ gemm_tc_kernel(const __grid_constant__ GemmLayer L) {
             uint32_t phase = 0;
             int acc = 0;
             uint32_t acc_phase = 0;
+            long long c_wait_op = 0, c_wait_tm = 0, c_kb = 0;
+            const long long c_start = clock64();
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
                 for (int kb0 = 0; kb0 < kblocks; kb0 += L.chunk_kblocks) {
                     const int kb1 = min(kb0 + L.chunk_kblocks, kblocks);
-                    mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1u);
+                    { const long long t0 = clock64(); mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1u); c_wait_tm += clock64() - t0; }
                     tc_fence_after();
                     const uint32_t tmem_d = tmem_base + (uint32_t)(acc * C::ACC_STRIDE);
                     for (int kb = kb0; kb < kb1; ++kb) {
-                        mbar_wait(&full_bar[stage], phase);
+                        { const long long t0 = clock64(); mbar_wait(&full_bar[stage], phase); c_wait_op += clock64() - t0; ++c_kb; }
                         tc_fence_after();
                         const uint32_t st = smem_u32(smem + stage * C::STAGE_BYTES);
                         const uint64_t da_hi = umma_desc_sw128(st);
@@ -178,6 +182,12 @@ gemm_tc_kernel(const __grid_constant__ GemmLayer L) {
                     if (acc == 0) acc_phase ^= 1u;
                 }
             }
+            if (L.dbg) {
+                atomicAdd(&L.dbg[0], (unsigned long long)(clock64() - c_start));
+                atomicAdd(&L.dbg[1], (unsigned long long)c_wait_op);
+                atomicAdd(&L.dbg[2], (unsigned long long)c_wait_tm);
+                atomicAdd(&L.dbg[3], (unsigned long long)c_kb);
+            }
         }
     } else {
         // ===================== epilogue (warps 2..5) =====================
@@ -185,6 +195,7 @@ gemm_tc_kernel(const __grid_constant__ GemmLayer L) {
         const int epi_tid = threadIdx.x - 64;
         int acc = 0;
         uint32_t acc_phase = 0;
+        long long c_epi_wait = 0, c_epi_drain = 0, c_epi_store = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
             const int g = tile / tiles_per_group;
             const int rem = tile - g * tiles_per_group;
@@ -200,7 +211,10 @@ gemm_tc_kernel(const __grid_constant__ GemmLayer L) {
 #pragma unroll
             for (int j = 0; j < BLOCK_N; ++j) sum[j] = 0.f;
             for (int kb0 = 0; kb0 < kblocks; kb0 += L.chunk_kblocks) {
+                long long t0 = clock64();
                 mbar_wait(&tmem_full_bar[acc], acc_phase);
+                const long long t1 = clock64();
+                c_epi_wait += t1 - t0;
                 tc_fence_after();
                 const uint32_t taddr0 =
                     tmem_base + (uint32_t)(acc * C::ACC_STRIDE) + ((uint32_t)(quarter * 32) << 16);
@@ -226,7 +240,9 @@ gemm_tc_kernel(const __grid_constant__ GemmLayer L) {
                 if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
                 acc ^= 1;
                 if (acc == 0) acc_phase ^= 1u;
+                c_epi_drain += clock64() - t1;
             }
+            const long long t_store = clock64();
 
             const long long row = (long long)m_tile * BLOCK_M + quarter * 32 + lane;
             bool store = row < L.m_rows;
@@ -272,6 +288,12 @@ gemm_tc_kernel(const __grid_constant__ GemmLayer L) {
                     }
                 }
             }
+            c_epi_store += clock64() - t_store;
+        }
+        if (L.dbg && warp == 2 && lane == 0) {
+            atomicAdd(&L.dbg[5], (unsigned long long)c_epi_wait);
+            atomicAdd(&L.dbg[6], (unsigned long long)c_epi_drain);
+            atomicAdd(&L.dbg[7], (unsigned long long)c_epi_store);
         }
     }
 

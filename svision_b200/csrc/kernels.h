@@ -43,9 +43,24 @@ struct GemmLayer {
     //   (m % pos_per_img) / grid_w < valid_h  &&  (m % pos_per_img) % grid_w < valid_w
     // pos_per_img == 0 disables the mask.
     int pos_per_img, grid_w, valid_h, valid_w;
+    // slab mode (conv_tc.cu): the A tensor maps have box rows = slab_rows and ONE slab
+    // [m0 + off_min, m0 + off_min + slab_rows) per (tile, channel block) feeds every tap
+    int use_slab;
+    int slab_rows;             // multiple of 8, >= 128 + max(row_off) - min(row_off), <= 256
+    int off_min;               // min(row_off)
+    int n_slab_slots, n_b_stages;
+    int desc_base_offset_mode; // 1: descriptor base_offset = (addr >> 7) & 7 for shifted starts
+    // optional cycle counters (development): 8 x unsigned long long, atomically accumulated per CTA
+    //  0 MMA-role total  1 MMA wait operands  2 MMA wait TMEM-empty  3 k-blocks
+    //  4 producer wait smem-empty  5 epilogue wait TMEM-full  6 epilogue drain  7 epilogue store
+    unsigned long long* dbg;
 };
 
 int launch_gemm_layer(const GemmLayer& L, int num_sms, cudaStream_t stream);
+// conv_tc.cu: same contract as launch_gemm_layer, slab pipeline (requires L.use_slab)
+int launch_conv_layer(const GemmLayer& L, int num_sms, cudaStream_t stream);
+// fills slab_rows / off_min / n_slab_slots / n_b_stages from taps, row_off, block_n, use_*_lo
+int plan_slab(GemmLayer& L);
 
 // Builds a 2-D tiled fp16 tensor map (SWIZZLE_128B, box = {64, box_rows}) over a row-major
 // [rows][cols] matrix with leading dimension ld (elements).

@@ -6,6 +6,7 @@
 #include "common.cuh"
 #include "kernels.h"
 
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <utility>
@@ -56,6 +57,9 @@ struct svx_handle {
     long long max_batch = 0;
     int precision = 0;
     bool has_model = false;
+    bool use_slab = true;                // conv_tc.cu (A halo slab) vs gemm_tc.cu (A tile per tap)
+    int desc_bo_mode = 0;                // measured on B200: swizzle uses absolute smem address bits, so
+                                         // row-shifted slab views need base_offset 0 (mode 1 is wrong)
     cudaStream_t stream = nullptr;       // used by svx_classify (host entry)
     long long last_n = 0;
 
@@ -83,6 +87,7 @@ struct svx_handle {
     float* probs_dev = nullptr;
 
     GemmLayer layer[L_COUNT];
+    unsigned long long* dbg = nullptr;   // [L_COUNT][8] cycle counters when SVX_DBG=1
 
     // optional per-kernel timing (svx_set_profiling)
     bool profiling = false;
@@ -174,10 +179,6 @@ int setup_layer(svx_handle* h, int li, const __half* a_hi, const __half* a_lo, l
     std::memset(&L, 0, sizeof(L));
     const long long K = (long long)s.taps * s.cg_pad;
     int rc;
-    if ((rc = make_tensor_map_2d(&L.tm_a_hi, a_hi, a_rows, lda, lda, GEMM_BLOCK_M))) return rc;
-    if ((rc = make_tensor_map_2d(&L.tm_a_lo, a_lo ? a_lo : a_hi, a_rows, lda, lda, GEMM_BLOCK_M))) return rc;
-    if ((rc = make_tensor_map_2d(&L.tm_b_hi, h->w_hi[li], s.n_total, K, K, s.block_n))) return rc;
-    if ((rc = make_tensor_map_2d(&L.tm_b_lo, h->w_lo[li], s.n_total, K, K, s.block_n))) return rc;
     L.block_n = s.block_n;
     L.chunk_kblocks = kChunkKBlocks;
     L.groups = s.groups;
@@ -202,7 +203,22 @@ int setup_layer(svx_handle* h, int li, const __half* a_hi, const __half* a_lo, l
     L.grid_w = grid_w;
     L.valid_h = valid_h;
     L.valid_w = valid_w;
+    int a_box_rows = GEMM_BLOCK_M;
+    if (h->use_slab) {
+        if ((rc = plan_slab(L))) return rc;
+        L.desc_base_offset_mode = h->desc_bo_mode;
+        a_box_rows = L.slab_rows;
+    }
+    if ((rc = make_tensor_map_2d(&L.tm_a_hi, a_hi, a_rows, lda, lda, a_box_rows))) return rc;
+    if ((rc = make_tensor_map_2d(&L.tm_a_lo, a_lo ? a_lo : a_hi, a_rows, lda, lda, a_box_rows))) return rc;
+    if ((rc = make_tensor_map_2d(&L.tm_b_hi, h->w_hi[li], s.n_total, K, K, s.block_n))) return rc;
+    if ((rc = make_tensor_map_2d(&L.tm_b_lo, h->w_lo[li], s.n_total, K, K, s.block_n))) return rc;
     return 0;
+}
+
+int run_layer(svx_handle* h, int li, cudaStream_t st) {
+    return h->use_slab ? launch_conv_layer(h->layer[li], h->num_sms, st)
+                       : launch_gemm_layer(h->layer[li], h->num_sms, st);
 }
 
 int build_model(svx_handle* h, const svx_weights* w) {
@@ -247,6 +263,10 @@ int build_model(svx_handle* h, const svx_weights* w) {
     if ((rc = setup_layer(h, L_CONV5, h->x5_hi, h->x5_lo, B * P3, 384, G3, 1, h->y5, nullptr, nullptr, 256, 0, 0, 0))) return rc;
     if ((rc = setup_layer(h, L_FC6, h->x6_hi, h->x6_lo, B, 9216, 1, 0, nullptr, h->x7_hi, h->x7_lo, 4096, 0, 0, 0))) return rc;
     if ((rc = setup_layer(h, L_FC7, h->x7_hi, h->x7_lo, B, 4096, 1, 0, nullptr, h->x8_hi, h->x8_lo, 4096, 0, 0, 0))) return rc;
+    if (std::getenv("SVX_DBG")) {
+        if ((rc = dev_alloc(h, &h->dbg, (size_t)L_COUNT * 8))) return rc;
+        for (int li = 0; li < L_COUNT; ++li) h->layer[li].dbg = h->dbg + li * 8;
+    }
     h->has_model = true;
     return 0;
 }
@@ -289,7 +309,7 @@ int run_cnn(svx_handle* h, long long n, int32_t* labels, float* probs, float* lo
     for (int li = 0; li < L_COUNT; ++li) h->layer[li].m_rows = rows[li];
 
     mark(h, 1, st);
-    if ((rc = launch_gemm_layer(h->layer[L_CONV1], h->num_sms, st))) return rc;
+    if ((rc = run_layer(h, L_CONV1, st))) return rc;
     PoolParams p1{};
     p1.in = h->y1; p1.in_grid_w = S2D; p1.in_pos_per_img = P1; p1.C = 96; p1.out_h = 27; p1.out_w = 27;
     p1.lrn = 1; p1.out_hi = h->x2_hi; p1.out_lo = h->x2_lo; p1.out_ld = 128; p1.out_grid_w = G2;
@@ -298,7 +318,7 @@ int run_cnn(svx_handle* h, long long n, int32_t* labels, float* probs, float* lo
     if ((rc = launch_pool(p1, n, h->num_sms, st))) return rc;
 
     mark(h, 3, st);
-    if ((rc = launch_gemm_layer(h->layer[L_CONV2], h->num_sms, st))) return rc;
+    if ((rc = run_layer(h, L_CONV2, st))) return rc;
     PoolParams p2{};
     p2.in = h->y2; p2.in_grid_w = G2; p2.in_pos_per_img = P2; p2.C = 256; p2.out_h = 13; p2.out_w = 13;
     p2.lrn = 1; p2.out_hi = h->x3_hi; p2.out_lo = h->x3_lo; p2.out_ld = 256; p2.out_grid_w = G3;
@@ -307,11 +327,11 @@ int run_cnn(svx_handle* h, long long n, int32_t* labels, float* probs, float* lo
     if ((rc = launch_pool(p2, n, h->num_sms, st))) return rc;
 
     mark(h, 5, st);
-    if ((rc = launch_gemm_layer(h->layer[L_CONV3], h->num_sms, st))) return rc;
+    if ((rc = run_layer(h, L_CONV3, st))) return rc;
     mark(h, 6, st);
-    if ((rc = launch_gemm_layer(h->layer[L_CONV4], h->num_sms, st))) return rc;
+    if ((rc = run_layer(h, L_CONV4, st))) return rc;
     mark(h, 7, st);
-    if ((rc = launch_gemm_layer(h->layer[L_CONV5], h->num_sms, st))) return rc;
+    if ((rc = run_layer(h, L_CONV5, st))) return rc;
     PoolParams p5{};
     p5.in = h->y5; p5.in_grid_w = G3; p5.in_pos_per_img = P3; p5.C = 256; p5.out_h = 6; p5.out_w = 6;
     p5.lrn = 0; p5.out_hi = h->x6_hi; p5.out_lo = h->x6_lo; p5.out_ld = 9216; p5.out_grid_w = 6;
@@ -320,9 +340,9 @@ int run_cnn(svx_handle* h, long long n, int32_t* labels, float* probs, float* lo
     if ((rc = launch_pool(p5, n, h->num_sms, st))) return rc;
 
     mark(h, 9, st);
-    if ((rc = launch_gemm_layer(h->layer[L_FC6], h->num_sms, st))) return rc;
+    if ((rc = run_layer(h, L_FC6, st))) return rc;
     mark(h, 10, st);
-    if ((rc = launch_gemm_layer(h->layer[L_FC7], h->num_sms, st))) return rc;
+    if ((rc = run_layer(h, L_FC7, st))) return rc;
     mark(h, 11, st);
     if ((rc = launch_fc8_softmax(h->x8_hi, h->x8_lo, h->w8, h->b8, n, labels, probs, logits, st))) return rc;
     mark(h, -1, st);
@@ -360,6 +380,8 @@ int svx_create(const svx_weights* weights, int device, int64_t max_batch, int pr
                                              "' is not sm_100 (this library has no other code path)");
     std::unique_ptr<svx_handle> h(new svx_handle());
     h->device = device;
+    if (const char* e = std::getenv("SVX_SLAB")) h->use_slab = std::atoi(e) != 0;
+    if (const char* e = std::getenv("SVX_DESC_BO")) h->desc_bo_mode = std::atoi(e);
     h->num_sms = prop.multiProcessorCount;
     h->max_batch = max_batch;
     h->precision = precision;
@@ -391,6 +413,16 @@ void svx_destroy(svx_handle* h) {
     for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
+}
+
+int svx_debug_counters(svx_handle* h, uint64_t* out, int reset) {
+    if (!h || !out) return fail(SVX_ERR_INVALID, "svx_debug_counters: bad arguments");
+    if (!h->dbg) return fail(SVX_ERR_INVALID, "svx_debug_counters: create the handle with SVX_DBG=1");
+    DeviceGuard guard(h->device);
+    SVX_CUDA_CHECK(cudaDeviceSynchronize());
+    SVX_CUDA_CHECK(cudaMemcpy(out, h->dbg, sizeof(uint64_t) * L_COUNT * 8, cudaMemcpyDeviceToHost));
+    if (reset) SVX_CUDA_CHECK(cudaMemset(h->dbg, 0, sizeof(uint64_t) * L_COUNT * 8));
+    return SVX_OK;
 }
 
 int svx_set_profiling(svx_handle* h, int enable) {
@@ -567,6 +599,58 @@ int svx_gemm_selftest(int device, const float* a_dev, const float* b_dev, float*
     L.use_a_lo = L.use_b_lo = precision == SVX_PRECISION_3PASS ? 1 : 0;
     L.m_rows = m; L.bias = bias; L.relu = 0; L.out_f32 = c_dev; L.ldc = (int)n;
     rc = launch_gemm_layer(L, prop.multiProcessorCount, st);
+    return free_all(rc);
+}
+
+int svx_conv_selftest(int device, const float* a_dev, const float* b_dev, float* c_dev, int64_t m,
+                      int64_t n, int64_t k_per_tap, int taps, const int* row_off, int block_n,
+                      int precision, int flags, void* stream) {
+    if (!a_dev || !b_dev || !c_dev || !row_off || m <= 0 || n <= 0 || k_per_tap <= 0 || taps < 1 ||
+        taps > GEMM_MAX_TAPS)
+        return fail(SVX_ERR_INVALID, "svx_conv_selftest: bad arguments");
+    if (k_per_tap % GEMM_BLOCK_K != 0 || n % block_n != 0)
+        return fail(SVX_ERR_INVALID, "svx_conv_selftest: k_per_tap % 64 or n % block_n != 0");
+    DeviceGuard guard(device);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    cudaDeviceProp prop;
+    SVX_CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) return fail(SVX_ERR_UNSUPPORTED, "svx_conv_selftest: device is not sm_100");
+    const int64_t k = k_per_tap * taps;
+    __half *a_hi = nullptr, *a_lo = nullptr, *b_hi = nullptr, *b_lo = nullptr;
+    float* bias = nullptr;
+    auto free_all = [&](int rc) {
+        cudaStreamSynchronize(st);
+        cudaFree(a_hi); cudaFree(a_lo); cudaFree(b_hi); cudaFree(b_lo); cudaFree(bias);
+        return rc;
+    };
+    SVX_CUDA_CHECK(cudaMalloc(&a_hi, (size_t)m * k_per_tap * 2));
+    SVX_CUDA_CHECK(cudaMalloc(&a_lo, (size_t)m * k_per_tap * 2));
+    SVX_CUDA_CHECK(cudaMalloc(&b_hi, (size_t)n * k * 2));
+    SVX_CUDA_CHECK(cudaMalloc(&b_lo, (size_t)n * k * 2));
+    SVX_CUDA_CHECK(cudaMalloc(&bias, (size_t)n * 4));
+    SVX_CUDA_CHECK(cudaMemsetAsync(bias, 0, (size_t)n * 4, st));
+    int rc;
+    if ((rc = launch_split_hilo(a_dev, m * k_per_tap, a_hi, a_lo, st))) return free_all(rc);
+    if ((rc = launch_split_hilo(b_dev, n * k, b_hi, b_lo, st))) return free_all(rc);
+    GemmLayer L;
+    std::memset(&L, 0, sizeof(L));
+    L.block_n = block_n; L.chunk_kblocks = kChunkKBlocks; L.groups = 1; L.n_per_group = (int)n;
+    L.taps = taps; L.cblocks = (int)(k_per_tap / GEMM_BLOCK_K); L.a_group_cols = 0;
+    for (int t = 0; t < taps; ++t) L.row_off[t] = row_off[t];
+    L.use_a_lo = L.use_b_lo = precision == SVX_PRECISION_3PASS ? 1 : 0;
+    L.m_rows = m; L.bias = bias; L.relu = 0; L.out_f32 = c_dev; L.ldc = (int)n;
+    int a_box = GEMM_BLOCK_M;
+    if (flags & 1) {
+        if ((rc = plan_slab(L))) return free_all(rc);
+        L.desc_base_offset_mode = (flags >> 1) & 1;
+        a_box = L.slab_rows;
+    }
+    if ((rc = make_tensor_map_2d(&L.tm_a_hi, a_hi, m, k_per_tap, k_per_tap, a_box))) return free_all(rc);
+    if ((rc = make_tensor_map_2d(&L.tm_a_lo, a_lo, m, k_per_tap, k_per_tap, a_box))) return free_all(rc);
+    if ((rc = make_tensor_map_2d(&L.tm_b_hi, b_hi, n, k, k, block_n))) return free_all(rc);
+    if ((rc = make_tensor_map_2d(&L.tm_b_lo, b_lo, n, k, k, block_n))) return free_all(rc);
+    rc = (flags & 1) ? launch_conv_layer(L, prop.multiProcessorCount, st)
+                     : launch_gemm_layer(L, prop.multiProcessorCount, st);
     return free_all(rc);
 }
 

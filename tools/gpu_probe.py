@@ -75,6 +75,36 @@ def stage_gemm():
                 return
 
 
+def stage_slab():
+    torch.manual_seed(1)
+    cases = [  # (m, n, k_per_tap, offsets, block_n)
+        (600, 128, 64, [0, 1, 2, 57, 58, 59, 114, 115, 116], 128),
+        (1000, 96, 64, [0, 1, 2, 57, 58, 59, 114, 115, 116], 96),
+        (2000, 128, 64, [(kh - 2) * 29 + (kw - 2) for kh in range(5) for kw in range(5)], 128),
+        (900, 256, 192, [(kh - 1) * 14 + (kw - 1) for kh in range(3) for kw in range(3)], 128),
+        (700, 128, 256, [0], 64),
+    ]
+    for (m, n, k, offs, bn) in cases:
+        a = torch.randn(m, k, device="cuda")
+        b = torch.randn(n, k * len(offs), device="cuda") * 0.05
+        ref = torch.zeros(m, n, dtype=torch.float64, device="cuda")
+        ad = a.double()
+        for t, off in enumerate(offs):
+            sh = torch.zeros_like(ad)
+            lo, hi = max(0, -off), min(m, m - off)
+            sh[lo:hi] = ad[lo + off:hi + off]
+            ref += sh @ b[:, t * k:(t + 1) * k].double().T
+        for slab, bo in ((False, 0), (True, 1), (True, 0)):
+            try:
+                c = C.conv_selftest(a, b, offs, block_n=bn, precision="3pass", slab=slab, base_offset_mode=bo)
+                torch.cuda.synchronize()
+                err = (c.double() - ref).abs().max().item()
+                print(f"conv m={m} n={n} k={k} taps={len(offs)} bn={bn} slab={slab} bo={bo}: max abs err {err:.3e} (ref max {ref.abs().max().item():.2f})", flush=True)
+            except Exception as ex:  # noqa: BLE001
+                print(f"conv m={m} n={n} k={k} taps={len(offs)} slab={slab} bo={bo}: FAILED {ex}", flush=True)
+                return
+
+
 def stage_cnn():
     from oracle import alexnet, encoder_c
     w = weights.synthetic_weights()
@@ -120,5 +150,31 @@ def stage_bench():
         clf.close()
 
 
+def stage_counters():
+    w = weights.synthetic_weights()
+    n = 2048
+    os.environ["SVX_DBG"] = "1"
+    for prec in ("3pass", "1pass"):
+        clf = C.Classifier(w, device=0, max_batch=2048, precision=prec)
+        rd = clf.rows_to_device(sites.make_sites_p1(n, seed=sites.SEED_CONFIG2))
+        for _ in range(2):
+            clf.classify_device(rd)
+        torch.cuda.synchronize()
+        clf.debug_counters(reset=True)
+        iters = 3
+        clf.set_profiling(True); clf.profile_read(True)
+        for _ in range(iters):
+            clf.classify_device(rd)
+        torch.cuda.synchronize()
+        prof = clf.profile_read(True)
+        c = clf.debug_counters().astype(np.float64)
+        names = ["conv1", "conv2", "conv3", "conv4", "conv5", "fc6", "fc7"]
+        print(f"[{prec}] slab={os.environ.get('SVX_SLAB','1')}  per-k-block cycles (avg over CTAs): total | wait operands | wait tmem | producer wait | epi: wait, drain, store (per k-block)   ms/launch")
+        for i, nm in enumerate(names):
+            kb = max(c[i, 3], 1)
+            print(f"  {nm:6s} kb/CTA={kb/iters/148:8.0f}  total={c[i,0]/kb:7.0f}  wait_op={c[i,1]/kb:7.0f}  wait_tm={c[i,2]/kb:7.0f}  prod_wait={c[i,4]/kb:7.0f}  epi_wait={c[i,5]/kb:7.0f} drain={c[i,6]/kb:7.0f} store={c[i,7]/kb:7.0f}   {prof[nm][0]/iters:.3f} ms", flush=True)
+        clf.close()
+
+
 if __name__ == "__main__":
-    {"encoder": stage_encoder, "gemm": stage_gemm, "cnn": stage_cnn, "bench": stage_bench}[sys.argv[1]]()
+    {"encoder": stage_encoder, "gemm": stage_gemm, "slab": stage_slab, "counters": stage_counters, "cnn": stage_cnn, "bench": stage_bench}[sys.argv[1]]()
