@@ -116,7 +116,8 @@ int svx_gemm_selftest(int device, const float *a_dev, const float *b_dev, float 
 
 /* Shifted-GEMM self-test: C[m][n] = sum_t sum_c A[m + row_off[t]][c] * B[n][t*k_per_tap + c]
  * (rows outside A read as zero).  flags bit0: slab kernel (conv_tc.cu) instead of the per-tap
- * kernel (gemm_tc.cu); bit1: descriptor base_offset mode for row-shifted slab views. */
+ * kernel (gemm_tc.cu); bit1: descriptor base_offset mode for row-shifted slab views; bit2: CTA-pair
+ * kernel (conv_tc2.cu, cta_group::2; block_n 128/192/256). */
 int svx_conv_selftest(int device, const float *a_dev, const float *b_dev, float *c_dev, int64_t m,
                       int64_t n, int64_t k_per_tap, int taps, const int *row_off, int block_n,
                       int precision, int flags, void *stream);

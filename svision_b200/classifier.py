@@ -200,7 +200,8 @@ def gemm_selftest(a: torch.Tensor, b: torch.Tensor, block_n: int = 128,
 
 
 def conv_selftest(a: torch.Tensor, b: torch.Tensor, row_off, block_n: int = 128,
-                  precision: str = "3pass", slab: bool = True, base_offset_mode: int = 1) -> torch.Tensor:
+                  precision: str = "3pass", slab: bool = True, base_offset_mode: int = 0,
+                  pair: bool = False) -> torch.Tensor:
     """C[m,n] = sum_t A[m + row_off[t], :] @ B[n, t*K:(t+1)*K].T through a tensor-core layer kernel
     (A [M,K], B [N,taps*K] float32 cuda tensors; rows outside A read as zero)."""
     lib = _lib.load()
@@ -211,7 +212,7 @@ def conv_selftest(a: torch.Tensor, b: torch.Tensor, row_off, block_n: int = 128,
     assert b.shape[1] == k * offs.size
     c = torch.empty((m, n), dtype=torch.float32, device=a.device)
     prec = {"3pass": _lib.PRECISION_3PASS, "1pass": _lib.PRECISION_1PASS}[precision]
-    flags = (1 if slab else 0) | ((base_offset_mode & 1) << 1)
+    flags = (1 if slab else 0) | ((base_offset_mode & 1) << 1) | (4 if pair else 0)
     _lib.check(lib.svx_conv_selftest(a.device.index or 0, a.data_ptr(), b.data_ptr(), c.data_ptr(),
                                      m, n, k, int(offs.size), offs.ctypes.data, block_n, prec, flags,
                                      torch.cuda.current_stream(a.device).cuda_stream),

@@ -1,0 +1,199 @@
+// Fused front end of the classify path: packed site row -> lit-pixel bitmap -> conv1 + ReLU ->
+// 3x3/2 max-pool -> LRN -> conv2 operand (fp16 hi/lo, padded layout), in ONE kernel; the 227x227x3
+// image, conv1's input tensor and conv1's 55x55x96 output never touch HBM.
+//
+// Replaces, for images produced by this library's own encoder:
+//   src/network/create_batch.py:103-152 + src/segmentplot/plot_segment.py:9-73   (image)
+//   src/network/alexnet.py:29-31: conv1 (11x11/4 VALID, 96) + ReLU, pool1, norm1
+//
+// Why this is exact and cheap.  After mean subtraction every pixel of channel c is lo_c or
+// lo_c + 255, so for every conv1 output
+//     conv1[Y,X,n] = base[n] + 255 * sum_{lit (r,c,ch) in the 11x11 window} W[r-4Y, c-4X, ch, n],
+//     base[n]      = bias[n] + sum_{kh,kw,ch} lo_ch * W[kh,kw,ch,n]          (host, in double)
+// -- the same dense convolution with its terms regrouped; only fp32 rounding order differs.  An
+// image has <= ~1100 lit channel-pixels of 154 587, so > 80 % of the pooled 27x27 positions see
+// pure background (one precomputed 96-vector) and the rest need a few dozen FMAs per channel
+// instead of 3 267 MACs.  The dense tcgen05 conv1 (conv_tc.cu) remains the path for arbitrary
+// images (svx_forward) and the parity tests cross-check the two.
+//
+// One CTA per site: bitmap in shared memory (encoder_bitmap.cuh, bit-exact with the reference
+// rasteriser); threads flag the pooled positions whose 19x19 receptive field holds a lit pixel;
+// background positions are streamed out with 16-byte stores; one warp per flagged position
+// walks the lit pixels of its field, lane = 3 consecutive output channels (weight reads are
+// coalesced over n), then max-pool, LRN by shuffle, fp16 hi/lo split.
+#include "common.cuh"
+#include "encoder_bitmap.cuh"
+#include "kernels.h"
+
+#include <math_constants.h>
+
+namespace svx {
+
+namespace {
+
+using namespace bitmap;
+
+constexpr int POOLED = 27;
+constexpr int NPOS = POOLED * POOLED;        // 729
+constexpr int G2W = 29, G2POS = G2W * G2W;   // conv2 operand grid (27 + 2 shared pad)
+constexpr int X2_LD = 128;                   // 2 groups x (48 real + 16 zero) channels
+
+// bits [c, c+19) of bitmap row r (c + 18 <= 226, so both words lie inside the row)
+__device__ __forceinline__ uint32_t window19(const uint32_t* plane, int r, int c) {
+    const uint32_t* rowp = plane + r * BMW;
+    const int wi = c >> 5;
+    return __funnelshift_r(rowp[wi], rowp[wi + 1], c & 31) & 0x7FFFFu;
+}
+
+// LRN over channels with lane = 3 consecutive channels (radius 2, alpha 2e-5, beta .75, bias 1)
+__device__ __forceinline__ void lrn3(const float (&m)[3], float (&out)[3], int lane) {
+    float sq[7];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) sq[j + 2] = m[j] * m[j];
+    const float l0 = __shfl_up_sync(0xffffffffu, sq[3], 1);
+    const float l1 = __shfl_up_sync(0xffffffffu, sq[4], 1);
+    const float r0 = __shfl_down_sync(0xffffffffu, sq[2], 1);
+    const float r1 = __shfl_down_sync(0xffffffffu, sq[3], 1);
+    sq[0] = lane > 0 ? l0 : 0.f;
+    sq[1] = lane > 0 ? l1 : 0.f;
+    sq[5] = lane < 31 ? r0 : 0.f;
+    sq[6] = lane < 31 ? r1 : 0.f;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        const float s5 = sq[j] + sq[j + 1] + sq[j + 2] + sq[j + 3] + sq[j + 4];
+        out[j] = m[j] * powf(1.0f + 2e-5f * s5, -0.75f);
+    }
+}
+
+__global__ void __launch_bounds__(ENC_THREADS)
+front_kernel(const int32_t* __restrict__ rows, long long n, const FrontParams P) {
+    __shared__ __align__(16) uint32_t bm[3 * PLANE];
+    __shared__ LineParams lines[2];
+    __shared__ uint32_t red[(ENC_THREADS / 32) * 8 * 2];
+    __shared__ uint32_t colmask[8];
+    __shared__ __align__(16) unsigned short bg[2][96];     // background vector: hi plane, lo plane
+    __shared__ uint32_t dirty_mask[(NPOS + 31) / 32];
+    __shared__ unsigned short dirty_list[NPOS];
+    __shared__ int dirty_count;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int c3 = 3 * lane;                                // this lane's first channel
+
+    // background value of every pooled position: LRN(ReLU(base)) (max-pool of a constant)
+    if (warp == 0) {
+        float m[3], o[3];
+#pragma unroll
+        for (int j = 0; j < 3; ++j) m[j] = fmaxf(P.base[c3 + j], 0.f);
+        lrn3(m, o, lane);
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            const __half h = __float2half_rn(o[j]);
+            bg[0][c3 + j] = __half_as_ushort(h);
+            bg[1][c3 + j] = __half_as_ushort(__float2half_rn(o[j] - __half2float(h)));
+        }
+    }
+
+    for (long long img = blockIdx.x; img < n; img += gridDim.x) {
+        if (tid < (NPOS + 31) / 32) dirty_mask[tid] = 0;
+        if (tid == 0) dirty_count = 0;
+        build_bitmap(rows + img * 12, bm, lines, red, colmask);      // ends with __syncthreads()
+
+        // ---- which pooled positions see a lit pixel? (receptive field: rows/cols 8p .. 8p+18)
+        for (int p = tid; p < NPOS; p += ENC_THREADS) {
+            const int py = p / POOLED, px = p - py * POOLED;
+            uint32_t any = 0;
+#pragma unroll
+            for (int dr = 0; dr < 19; ++dr) any |= window19(bm, 8 * py + dr, 8 * px);
+            if (any) {
+                atomicOr(&dirty_mask[p >> 5], 1u << (p & 31));
+                dirty_list[atomicAdd(&dirty_count, 1)] = (unsigned short)p;
+            }
+        }
+        __syncthreads();
+
+        // ---- background positions: 12 channel octets x 2 planes per position, 16-byte stores
+        __half* const planes[2] = {P.x2_hi, P.x2_lo};
+        const long long img_row0 = img * G2POS;
+        for (int v = tid; v < NPOS * 24; v += ENC_THREADS) {
+            const int plane = v >= NPOS * 12;
+            const int rem = v - plane * NPOS * 12;
+            const int p = rem / 12, o = rem - p * 12;
+            if ((dirty_mask[p >> 5] >> (p & 31)) & 1u) continue;
+            const int py = p / POOLED, px = p - py * POOLED;
+            const uint4 val = *reinterpret_cast<const uint4*>(&bg[plane][8 * o]);
+            const long long off =
+                (img_row0 + py * G2W + px) * X2_LD + (o / 6) * 64 + (o % 6) * 8;
+            *reinterpret_cast<uint4*>(planes[plane] + off) = val;
+        }
+
+        // ---- flagged positions: one warp each
+        const int nd = dirty_count;
+        for (int i = warp; i < nd; i += ENC_THREADS / 32) {
+            const int p = dirty_list[i];
+            const int py = p / POOLED, px = p - py * POOLED;
+            const int r0 = 8 * py, c0 = 8 * px;
+            float acc[9][3];
+#pragma unroll
+            for (int q = 0; q < 9; ++q)
+#pragma unroll
+                for (int j = 0; j < 3; ++j) acc[q][j] = P.base[c3 + j];
+            for (int dr = 0; dr < 19; ++dr) {
+                uint32_t w0 = window19(bm, r0 + dr, c0);
+                if (!w0) continue;
+                const uint32_t w1 = window19(bm + PLANE, r0 + dr, c0);
+                const uint32_t w2 = window19(bm + 2 * PLANE, r0 + dr, c0);
+                while (w0) {
+                    const int dc = __ffs(w0) - 1;
+                    w0 &= w0 - 1;
+                    const bool l1 = (w1 >> dc) & 1u, l2 = (w2 >> dc) & 1u;
+#pragma unroll
+                    for (int a = 0; a < 3; ++a) {
+                        const int kh = dr - 4 * a;
+                        if (kh < 0 || kh > 10) continue;
+#pragma unroll
+                        for (int b = 0; b < 3; ++b) {
+                            const int kw = dc - 4 * b;
+                            if (kw < 0 || kw > 10) continue;
+                            const float* wp = P.w255 + ((kh * 11 + kw) * 3) * 96 + c3;
+                            float d0 = __ldg(wp), d1 = __ldg(wp + 1), d2 = __ldg(wp + 2);
+                            if (l1) { d0 += __ldg(wp + 96); d1 += __ldg(wp + 97); d2 += __ldg(wp + 98); }
+                            if (l2) { d0 += __ldg(wp + 192); d1 += __ldg(wp + 193); d2 += __ldg(wp + 194); }
+                            acc[a * 3 + b][0] += d0;
+                            acc[a * 3 + b][1] += d1;
+                            acc[a * 3 + b][2] += d2;
+                        }
+                    }
+                }
+            }
+            float m[3] = {0.f, 0.f, 0.f}, o[3];              // ReLU folded into the max with 0
+#pragma unroll
+            for (int q = 0; q < 9; ++q)
+#pragma unroll
+                for (int j = 0; j < 3; ++j) m[j] = fmaxf(m[j], acc[q][j]);
+            lrn3(m, o, lane);
+            const long long off =
+                (img_row0 + py * G2W + px) * X2_LD + (c3 / 48) * 64 + (c3 % 48);
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+                const __half h = __float2half_rn(o[j]);
+                P.x2_hi[off + j] = h;
+                P.x2_lo[off + j] = __float2half_rn(o[j] - __half2float(h));
+            }
+        }
+        __syncthreads();
+    }
+}
+
+}  // namespace
+
+int launch_front(const int32_t* rows_dev, long long n, const FrontParams& P, int num_sms,
+                 cudaStream_t stream) {
+    if (n <= 0) return 0;
+    long long blocks = (long long)num_sms * 6;
+    if (blocks > n) blocks = n;
+    front_kernel<<<(unsigned)blocks, bitmap::ENC_THREADS, 0, stream>>>(rows_dev, n, P);
+    SVX_LAUNCH_CHECK("front_kernel");
+    return 0;
+}
+
+}  // namespace svx

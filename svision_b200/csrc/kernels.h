@@ -12,6 +12,17 @@ namespace svx {
 int launch_encode(const int32_t* rows_dev, long long n, void* out, int mode, int num_sms,
                   cudaStream_t stream);
 
+// ---- front.cu ---------------------------------------------------------------------------------
+// Fused encode + conv1 + ReLU + pool1 + LRN1 for encoder-generated images (sparse update form).
+struct FrontParams {
+    const float* w255;         // [11][11][3][96] = 255 * conv1 weights (TF layout)
+    const float* base;         // [96] = bias + sum_k lo_ch * W[k]  (conv1 of the all-background image)
+    __half* x2_hi;             // conv2 operand [n*841][128], see DESIGN.md §3
+    __half* x2_lo;
+};
+int launch_front(const int32_t* rows_dev, long long n, const FrontParams& P, int num_sms,
+                 cudaStream_t stream);
+
 // ---- gemm_tc.cu -------------------------------------------------------------------------------
 constexpr int GEMM_BLOCK_M = 128;
 constexpr int GEMM_BLOCK_K = 64;
@@ -61,6 +72,9 @@ int launch_gemm_layer(const GemmLayer& L, int num_sms, cudaStream_t stream);
 int launch_conv_layer(const GemmLayer& L, int num_sms, cudaStream_t stream);
 // fills slab_rows / off_min / n_slab_slots / n_b_stages from taps, row_off, block_n, use_*_lo
 int plan_slab(GemmLayer& L);
+// conv_tc2.cu: CTA-pair (cta_group::2) kernel; the weight tensor maps must have box rows = block_n/2
+int launch_conv_layer_pair(const GemmLayer& L, int num_sms, cudaStream_t stream);
+int plan_slab_pair(GemmLayer& L);
 
 // Builds a 2-D tiled fp16 tensor map (SWIZZLE_128B, box = {64, box_rows}) over a row-major
 // [rows][cols] matrix with leading dimension ld (elements).

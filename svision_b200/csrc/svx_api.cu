@@ -36,15 +36,16 @@ enum { L_CONV1 = 0, L_CONV2, L_CONV3, L_CONV4, L_CONV5, L_FC6, L_FC7, L_COUNT };
 
 struct LayerSpec {
     int taps, cg_real, cg_pad, groups, n_total, block_n, kh, kw;
+    int block_n_pair;          // N-tile of the CTA-pair kernel (0: layer stays on the 1-CTA kernel)
 };
 static const LayerSpec kSpec[L_COUNT] = {
-    /* conv1 (s2d) */ {9, 48, 64, 1, 96, 96, 3, 3},
-    /* conv2       */ {25, 48, 64, 2, 256, 128, 5, 5},
-    /* conv3       */ {9, 256, 256, 1, 384, 128, 3, 3},
-    /* conv4       */ {9, 192, 192, 2, 384, 96, 3, 3},
-    /* conv5       */ {9, 192, 192, 2, 256, 128, 3, 3},
-    /* fc6         */ {1, 9216, 9216, 1, 4096, 128, 1, 1},
-    /* fc7         */ {1, 4096, 4096, 1, 4096, 128, 1, 1},
+    /* conv1 (s2d) */ {9, 48, 64, 1, 96, 96, 3, 3, 0},
+    /* conv2       */ {25, 48, 64, 2, 256, 128, 5, 5, 128},
+    /* conv3       */ {9, 256, 256, 1, 384, 128, 3, 3, 192},
+    /* conv4       */ {9, 192, 192, 2, 384, 96, 3, 3, 192},
+    /* conv5       */ {9, 192, 192, 2, 256, 128, 3, 3, 128},
+    /* fc6         */ {1, 9216, 9216, 1, 4096, 128, 1, 1, 256},
+    /* fc7         */ {1, 4096, 4096, 1, 4096, 128, 1, 1, 256},
 };
 
 }  // namespace svx
@@ -57,6 +58,10 @@ struct svx_handle {
     long long max_batch = 0;
     int precision = 0;
     bool has_model = false;
+    bool use_front = true;               // fused sparse front end (front.cu) in the classify path
+    float* front_w255 = nullptr;
+    float* front_base = nullptr;
+    bool use_pair = true;                // conv_tc2.cu (cta_group::2) where the layer supports it
     bool use_slab = true;                // conv_tc.cu (A halo slab) vs gemm_tc.cu (A tile per tap)
     int desc_bo_mode = 0;                // measured on B200: swizzle uses absolute smem address bits, so
                                          // row-shifted slab views need base_offset 0 (mode 1 is wrong)
@@ -203,22 +208,30 @@ int setup_layer(svx_handle* h, int li, const __half* a_hi, const __half* a_lo, l
     L.grid_w = grid_w;
     L.valid_h = valid_h;
     L.valid_w = valid_w;
-    int a_box_rows = GEMM_BLOCK_M;
-    if (h->use_slab) {
+    int a_box_rows = GEMM_BLOCK_M, b_box_rows = s.block_n;
+    if (h->use_slab && h->use_pair && s.block_n_pair > 0) {
+        L.block_n = s.block_n_pair;
+        if ((rc = plan_slab_pair(L))) return rc;
+        L.desc_base_offset_mode = h->desc_bo_mode;
+        a_box_rows = L.slab_rows;
+        b_box_rows = L.block_n / 2;
+    } else if (h->use_slab) {
         if ((rc = plan_slab(L))) return rc;
         L.desc_base_offset_mode = h->desc_bo_mode;
         a_box_rows = L.slab_rows;
     }
     if ((rc = make_tensor_map_2d(&L.tm_a_hi, a_hi, a_rows, lda, lda, a_box_rows))) return rc;
     if ((rc = make_tensor_map_2d(&L.tm_a_lo, a_lo ? a_lo : a_hi, a_rows, lda, lda, a_box_rows))) return rc;
-    if ((rc = make_tensor_map_2d(&L.tm_b_hi, h->w_hi[li], s.n_total, K, K, s.block_n))) return rc;
-    if ((rc = make_tensor_map_2d(&L.tm_b_lo, h->w_lo[li], s.n_total, K, K, s.block_n))) return rc;
+    if ((rc = make_tensor_map_2d(&L.tm_b_hi, h->w_hi[li], s.n_total, K, K, b_box_rows))) return rc;
+    if ((rc = make_tensor_map_2d(&L.tm_b_lo, h->w_lo[li], s.n_total, K, K, b_box_rows))) return rc;
     return 0;
 }
 
 int run_layer(svx_handle* h, int li, cudaStream_t st) {
-    return h->use_slab ? launch_conv_layer(h->layer[li], h->num_sms, st)
-                       : launch_gemm_layer(h->layer[li], h->num_sms, st);
+    const GemmLayer& L = h->layer[li];
+    if (L.use_slab == 2) return launch_conv_layer_pair(L, h->num_sms, st);
+    if (L.use_slab == 1) return launch_conv_layer(L, h->num_sms, st);
+    return launch_gemm_layer(L, h->num_sms, st);
 }
 
 int build_model(svx_handle* h, const svx_weights* w) {
@@ -235,6 +248,22 @@ int build_model(svx_handle* h, const svx_weights* w) {
     if ((rc = dev_alloc(h, &h->b8, (size_t)5, false))) return rc;
     SVX_CUDA_CHECK(cudaMemcpy(h->w8, w->fc8_w, 4096 * 5 * sizeof(float), cudaMemcpyHostToDevice));
     SVX_CUDA_CHECK(cudaMemcpy(h->b8, w->fc8_b, 5 * sizeof(float), cudaMemcpyHostToDevice));
+
+    {   // fused front end: 255*W1 and the conv1 response to the all-background image
+        const float lo[3] = {-104.f, -117.f, -124.f};               // create_batch.py:13,147-150
+        std::vector<float> w255((size_t)11 * 11 * 3 * 96), base(96);
+        for (int nn = 0; nn < 96; ++nn) {
+            double acc = w->conv1_b[nn];
+            for (int k = 0; k < 121; ++k)
+                for (int c = 0; c < 3; ++c) acc += (double)lo[c] * (double)w->conv1_w[((size_t)k * 3 + c) * 96 + nn];
+            base[nn] = (float)acc;
+        }
+        for (size_t i = 0; i < w255.size(); ++i) w255[i] = 255.f * w->conv1_w[i];
+        if ((rc = dev_alloc(h, &h->front_w255, w255.size(), false))) return rc;
+        if ((rc = dev_alloc(h, &h->front_base, base.size(), false))) return rc;
+        SVX_CUDA_CHECK(cudaMemcpy(h->front_w255, w255.data(), w255.size() * sizeof(float), cudaMemcpyHostToDevice));
+        SVX_CUDA_CHECK(cudaMemcpy(h->front_base, base.data(), base.size() * sizeof(float), cudaMemcpyHostToDevice));
+    }
 
     // activations: zero once; pad positions/channels are never written afterwards
     if ((rc = dev_alloc(h, &h->y1, (size_t)B * P1 * 96))) return rc;
@@ -303,11 +332,12 @@ int profile_collect(svx_handle* h) {
 
 // x1 (conv1 operand) of `n` sites is resident -> labels / probs / logits
 int run_cnn(svx_handle* h, long long n, int32_t* labels, float* probs, float* logits,
-            cudaStream_t st) {
+            cudaStream_t st, bool x2_ready = false) {
     int rc;
     const long long rows[L_COUNT] = {n * P1, n * P2, n * P3, n * P3, n * P3, n, n};
     for (int li = 0; li < L_COUNT; ++li) h->layer[li].m_rows = rows[li];
 
+    if (!x2_ready) {
     mark(h, 1, st);
     if ((rc = run_layer(h, L_CONV1, st))) return rc;
     PoolParams p1{};
@@ -316,6 +346,7 @@ int run_cnn(svx_handle* h, long long n, int32_t* labels, float* probs, float* lo
     p1.out_pos_per_img = P2; p1.group_real = 48; p1.group_pad = 64; p1.flatten = 0;
     mark(h, 2, st);
     if ((rc = launch_pool(p1, n, h->num_sms, st))) return rc;
+    }
 
     mark(h, 3, st);
     if ((rc = run_layer(h, L_CONV2, st))) return rc;
@@ -350,6 +381,15 @@ int run_cnn(svx_handle* h, long long n, int32_t* labels, float* probs, float* lo
     return 0;
 }
 
+// rows -> conv2 operand (fused sparse front end) or rows -> conv1 operand (dense path)
+int encode_front(svx_handle* h, const int32_t* rows_dev, long long m, cudaStream_t st) {
+    if (h->use_front) {
+        FrontParams fp{h->front_w255, h->front_base, h->x2_hi, h->x2_lo};
+        return launch_front(rows_dev, m, fp, h->num_sms, st);
+    }
+    return launch_encode(rows_dev, m, h->x1, 2, h->num_sms, st);
+}
+
 }  // namespace
 
 extern "C" {
@@ -381,6 +421,8 @@ int svx_create(const svx_weights* weights, int device, int64_t max_batch, int pr
     std::unique_ptr<svx_handle> h(new svx_handle());
     h->device = device;
     if (const char* e = std::getenv("SVX_SLAB")) h->use_slab = std::atoi(e) != 0;
+    if (const char* e = std::getenv("SVX_FRONT")) h->use_front = std::atoi(e) != 0;
+    if (const char* e = std::getenv("SVX_PAIR")) h->use_pair = std::atoi(e) != 0;
     if (const char* e = std::getenv("SVX_DESC_BO")) h->desc_bo_mode = std::atoi(e);
     h->num_sms = prop.multiProcessorCount;
     h->max_batch = max_batch;
@@ -486,9 +528,9 @@ int svx_classify_device(svx_handle* h, const int32_t* rows_dev, int64_t n, int32
         const int64_t m = n - s < h->max_batch ? n - s : h->max_batch;
         int rc;
         mark(h, 0, st);
-        if ((rc = launch_encode(rows_dev + s * SVX_ROW_FIELDS, m, h->x1, 2, h->num_sms, st))) return rc;
+        if ((rc = encode_front(h, rows_dev + s * SVX_ROW_FIELDS, m, st))) return rc;
         if ((rc = run_cnn(h, m, labels_dev + s, probs_dev + s * SVX_NUM_CLASSES,
-                          logits_dev ? logits_dev + s * SVX_NUM_CLASSES : nullptr, st)))
+                          logits_dev ? logits_dev + s * SVX_NUM_CLASSES : nullptr, st, h->use_front)))
             return rc;
     }
     return SVX_OK;
@@ -507,8 +549,8 @@ int svx_classify(svx_handle* h, const int32_t* rows_host, int64_t n, int32_t* la
         SVX_CUDA_CHECK(cudaMemcpyAsync(h->rows_dev, rows_host + s * SVX_ROW_FIELDS,
                                        (size_t)m * SVX_ROW_FIELDS * sizeof(int32_t), cudaMemcpyHostToDevice, st));
         mark(h, 0, st);
-        if ((rc = launch_encode(h->rows_dev, m, h->x1, 2, h->num_sms, st))) return rc;
-        if ((rc = run_cnn(h, m, h->labels_dev, h->probs_dev, nullptr, st))) return rc;
+        if ((rc = encode_front(h, h->rows_dev, m, st))) return rc;
+        if ((rc = run_cnn(h, m, h->labels_dev, h->probs_dev, nullptr, st, h->use_front))) return rc;
         SVX_CUDA_CHECK(cudaMemcpyAsync(labels_host + s, h->labels_dev, (size_t)m * sizeof(int32_t),
                                        cudaMemcpyDeviceToHost, st));
         SVX_CUDA_CHECK(cudaMemcpyAsync(probs_host + s * SVX_NUM_CLASSES, h->probs_dev,
@@ -639,18 +681,23 @@ int svx_conv_selftest(int device, const float* a_dev, const float* b_dev, float*
     for (int t = 0; t < taps; ++t) L.row_off[t] = row_off[t];
     L.use_a_lo = L.use_b_lo = precision == SVX_PRECISION_3PASS ? 1 : 0;
     L.m_rows = m; L.bias = bias; L.relu = 0; L.out_f32 = c_dev; L.ldc = (int)n;
-    int a_box = GEMM_BLOCK_M;
-    if (flags & 1) {
+    int a_box = GEMM_BLOCK_M, b_box = block_n;
+    if (flags & 4) {
+        if ((rc = plan_slab_pair(L))) return free_all(rc);
+        a_box = L.slab_rows;
+        b_box = block_n / 2;
+    } else if (flags & 1) {
         if ((rc = plan_slab(L))) return free_all(rc);
         L.desc_base_offset_mode = (flags >> 1) & 1;
         a_box = L.slab_rows;
     }
     if ((rc = make_tensor_map_2d(&L.tm_a_hi, a_hi, m, k_per_tap, k_per_tap, a_box))) return free_all(rc);
     if ((rc = make_tensor_map_2d(&L.tm_a_lo, a_lo, m, k_per_tap, k_per_tap, a_box))) return free_all(rc);
-    if ((rc = make_tensor_map_2d(&L.tm_b_hi, b_hi, n, k, k, block_n))) return free_all(rc);
-    if ((rc = make_tensor_map_2d(&L.tm_b_lo, b_lo, n, k, k, block_n))) return free_all(rc);
-    rc = (flags & 1) ? launch_conv_layer(L, prop.multiProcessorCount, st)
-                     : launch_gemm_layer(L, prop.multiProcessorCount, st);
+    if ((rc = make_tensor_map_2d(&L.tm_b_hi, b_hi, n, k, k, b_box))) return free_all(rc);
+    if ((rc = make_tensor_map_2d(&L.tm_b_lo, b_lo, n, k, k, b_box))) return free_all(rc);
+    rc = (flags & 4) ? launch_conv_layer_pair(L, prop.multiProcessorCount, st)
+         : (flags & 1) ? launch_conv_layer(L, prop.multiProcessorCount, st)
+                       : launch_gemm_layer(L, prop.multiProcessorCount, st);
     return free_all(rc);
 }
 

@@ -34,17 +34,44 @@ def clf(synthetic_weights):
     c.close()
 
 
+LAYERS = ("norm1", "conv2", "norm2", "conv3", "conv4", "conv5", "pool5", "fc6", "fc7")
+
+
+def _check_layers(clf, inter, n, names):
+    for name in names:
+        got = clf.debug_activation(name, n)
+        ref = inter[name].numpy()
+        scale = np.abs(ref).max()
+        assert np.abs(got - ref).max() < 2e-4 * scale + 1e-5, name
+
+
 def test_layerwise_activations_match_oracle(clf, cnn_golden, synthetic_weights):
     rows = cnn_golden["rows"][:16]
     imgs = encoder_c.encode_f32(rows)
     _, inter = alexnet.forward(imgs, synthetic_weights, torch.float32, return_intermediates=True)
+    # classify path: fused sparse front end (rows -> norm1) + tensor-core layers
     clf.classify_device(clf.rows_to_device(rows))
     torch.cuda.synchronize()
-    for name in ("conv1", "norm1", "conv2", "norm2", "conv3", "conv4", "conv5", "pool5", "fc6", "fc7"):
-        got = clf.debug_activation(name, rows.shape[0])
-        ref = inter[name].numpy()
-        scale = np.abs(ref).max()
-        assert np.abs(got - ref).max() < 2e-4 * scale + 1e-5, name
+    _check_layers(clf, inter, rows.shape[0], LAYERS)
+    # forward path on materialised images: dense tcgen05 conv1 + pool1/LRN1 kernels
+    clf.forward(torch.from_numpy(imgs).cuda())
+    torch.cuda.synchronize()
+    _check_layers(clf, inter, rows.shape[0], ("conv1",) + LAYERS)
+
+
+def test_fused_front_end_matches_dense_path(cnn_golden, synthetic_weights, monkeypatch):
+    rows = np.concatenate([sites.edge_case_sites(), cnn_golden["rows"][:50]])
+    out = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("SVX_FRONT", mode)
+        with C.Classifier(synthetic_weights, device=0, max_batch=64) as c:
+            labels, probs, logits = c.classify_device(c.rows_to_device(rows), want_logits=True)
+            out[mode] = (labels.cpu().numpy(), probs.cpu().numpy(), logits.cpu().numpy(),
+                         c.debug_activation("norm1", rows.shape[0]))
+    assert np.array_equal(out["1"][0], out["0"][0])
+    assert np.abs(out["1"][3] - out["0"][3]).max() < 1e-3          # norm1, values up to ~140
+    assert np.abs(out["1"][2] - out["0"][2]).max() < 1e-3          # logits
+    assert np.abs(out["1"][1] - out["0"][1]).max() < 2e-4          # softmax
 
 
 def test_labels_and_softmax_match_oracle(clf, cnn_golden):
@@ -74,9 +101,11 @@ def test_forward_on_encoder_images_equals_fused_path(clf, cnn_golden):
     rows = cnn_golden["rows"][:48]
     rd = clf.rows_to_device(rows)
     _, _, logits = clf.classify_device(rd, want_logits=True)
-    for dt in (torch.float16, torch.float32):
-        l2 = clf.forward(clf.encode(rd, dtype=dt))
-        assert torch.equal(l2, logits)
+    l16 = clf.forward(clf.encode(rd, dtype=torch.float16))
+    l32 = clf.forward(clf.encode(rd, dtype=torch.float32))
+    assert torch.equal(l16, l32)                       # both image dtypes are lossless
+    # dense conv1 (forward) vs fused sparse front end (classify): same maths, different fp32 order
+    assert (l16 - logits).abs().max().item() < 1e-3
 
 
 def test_results_independent_of_batch_position(clf, cnn_golden):

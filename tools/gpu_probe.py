@@ -83,6 +83,7 @@ def stage_slab():
         (2000, 128, 64, [(kh - 2) * 29 + (kw - 2) for kh in range(5) for kw in range(5)], 128),
         (900, 256, 192, [(kh - 1) * 14 + (kw - 1) for kh in range(3) for kw in range(3)], 128),
         (700, 128, 256, [0], 64),
+        (5000, 512, 1024, [0], 128),
     ]
     for (m, n, k, offs, bn) in cases:
         a = torch.randn(m, k, device="cuda")
@@ -94,14 +95,16 @@ def stage_slab():
             lo, hi = max(0, -off), min(m, m - off)
             sh[lo:hi] = ad[lo + off:hi + off]
             ref += sh @ b[:, t * k:(t + 1) * k].double().T
-        for slab, bo in ((False, 0), (True, 1), (True, 0)):
+        for slab, pair in ((False, False), (True, False), (True, True)):
+            if pair and (n % 128 != 0):
+                continue
             try:
-                c = C.conv_selftest(a, b, offs, block_n=bn, precision="3pass", slab=slab, base_offset_mode=bo)
+                c = C.conv_selftest(a, b, offs, block_n=(128 if pair else bn), precision="3pass", slab=slab, pair=pair)
                 torch.cuda.synchronize()
                 err = (c.double() - ref).abs().max().item()
-                print(f"conv m={m} n={n} k={k} taps={len(offs)} bn={bn} slab={slab} bo={bo}: max abs err {err:.3e} (ref max {ref.abs().max().item():.2f})", flush=True)
+                print(f"conv m={m} n={n} k={k} taps={len(offs)} bn={bn} slab={slab} pair={pair}: max abs err {err:.3e} (ref max {ref.abs().max().item():.2f})", flush=True)
             except Exception as ex:  # noqa: BLE001
-                print(f"conv m={m} n={n} k={k} taps={len(offs)} slab={slab} bo={bo}: FAILED {ex}", flush=True)
+                print(f"conv m={m} n={n} k={k} taps={len(offs)} slab={slab} pair={pair}: FAILED {ex}", flush=True)
                 return
 
 
@@ -118,7 +121,7 @@ def stage_cnn():
         rd = clf.rows_to_device(rows)
         labels, probs, logits = clf.classify_device(rd, want_logits=True)
         torch.cuda.synchronize()
-        for name in ("conv1", "norm1", "conv2", "norm2", "conv3", "conv4", "conv5", "pool5", "fc6", "fc7"):
+        for name in ("norm1", "conv2", "norm2", "conv3", "conv4", "conv5", "pool5", "fc6", "fc7"):
             got = clf.debug_activation(name, rows.shape[0])
             ref = inter[name].numpy()
             err = np.abs(got - ref).max()
@@ -132,6 +135,8 @@ def stage_cnn():
         im16 = clf.encode(rd, dtype=torch.float16)
         l2 = clf.forward(im16)
         print(f"[{prec}] forward(images) vs classify logits max diff {(l2 - logits).abs().max().item():.3e}", flush=True)
+        got = clf.debug_activation("conv1", rows.shape[0]); ref = inter["conv1"].numpy()
+        print(f"  [{prec}] dense conv1 (forward path) max abs err {np.abs(got-ref).max():.3e}", flush=True)
         clf.close()
 
 
