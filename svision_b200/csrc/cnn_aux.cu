@@ -84,8 +84,8 @@ __global__ void __launch_bounds__(256) pool_kernel(const PoolParams p, long long
             if (p.flatten) {
                 o = img * (long long)p.out_ld + (long long)(y * p.out_w + x) * p.C + c0;
             } else {
-                const int col = (c0 / p.group_real) * p.group_pad + (c0 % p.group_real);
-                o = (img * p.out_pos_per_img + (long long)y * p.out_grid_w + x) * p.out_ld + col;
+                o = (long long)(c0 / p.group_real) * p.group_elems +
+                    (img * p.out_pos_per_img + (long long)y * p.out_grid_w + x) * p.out_ld + (c0 % p.group_real);
             }
             uint32_t ph[CPL / 2], pl[CPL / 2];
 #pragma unroll
@@ -192,7 +192,8 @@ int launch_pool(const PoolParams& p, long long n_img, int num_sms, cudaStream_t 
     const long long total = n_img * p.out_h * p.out_w;
     if (total <= 0) return 0;
     const int cpl = p.C <= 128 ? 4 : 8;
-    if (p.C % cpl != 0 || p.C / cpl > 32 || p.group_real % cpl != 0 || p.group_pad % cpl != 0)
+    if (p.C % cpl != 0 || p.C / cpl > 32 || p.group_real % cpl != 0 || p.group_elems % cpl != 0 ||
+        p.out_ld % cpl != 0)
         return fail(-1, "pool: unsupported channel count / grouping");
     long long blocks = (long long)num_sms * 8;           // 8 CTAs x 8 warps resident per SM
     if (blocks > (total + 7) / 8) blocks = (total + 7) / 8;

@@ -118,6 +118,7 @@ conv_tc_kernel(const __grid_constant__ GemmLayer L) {
             const int m0 = m_tile * BLOCK_M;
             const int n0 = g * L.n_per_group + n_tile * BLOCK_N;
             const int a_col0 = g * L.a_group_cols;
+            const int a_row0 = g * L.a_group_rows + L.a_row_bias + L.off_min;
             for (int cb = 0; cb < L.cblocks; ++cb) {
                 long long t0 = 0;
                 if (DBG) t0 = clock64();
@@ -126,10 +127,10 @@ conv_tc_kernel(const __grid_constant__ GemmLayer L) {
                 if (elect_one()) {
                     uint8_t* sl = smem + slot * slab_slot_bytes;
                     mbar_arrive_expect_tx(&full_s[slot], (uint32_t)slab_slot_bytes);
-                    tma_load_2d(&L.tm_a_hi, &full_s[slot], sl, a_col0 + cb * BLOCK_K, m0 + L.off_min);
+                    tma_load_2d(&L.tm_a_hi, &full_s[slot], sl, a_col0 + cb * BLOCK_K, m0 + a_row0);
                     if (A_LO)
                         tma_load_2d(&L.tm_a_lo, &full_s[slot], sl + slab_plane, a_col0 + cb * BLOCK_K,
-                                    m0 + L.off_min);
+                                    m0 + a_row0);
                 }
                 __syncwarp();
                 if (++slot == L.n_slab_slots) { slot = 0; slot_phase ^= 1u; }
@@ -183,8 +184,10 @@ conv_tc_kernel(const __grid_constant__ GemmLayer L) {
                         // slab row shift of this tap: 128 B per row -> 8 descriptor units per row
                         const uint32_t a_lo32 = slab_lo + (uint32_t)((L.row_off[t] - L.off_min) * 8);
                         const uint32_t b_lo32 = desc_lo(smem_u32(smem_b + stage * b_stage_bytes));
+                        const int nk = (cb + 1 == L.cblocks) ? L.last_ksteps : BLOCK_K / UMMA_K;
 #pragma unroll
                         for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+                            if (k >= nk) break;
                             const uint32_t ko = (uint32_t)(k * UMMA_K * 2 / 16);   // 32 B per k-step
                             const uint64_t da = make_desc(a_lo32 + ko);
                             const uint64_t db = make_desc(b_lo32 + ko);

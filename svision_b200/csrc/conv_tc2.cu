@@ -128,6 +128,7 @@ conv_tc2_kernel(const __grid_constant__ GemmLayer L) {
             const int m0 = mp_tile * 2 * BLOCK_M + (int)rank * BLOCK_M;       // this CTA's rows
             const int n0 = g * L.n_per_group + n_tile * BLOCK_N + (int)rank * HALF_N;   // its weight rows
             const int a_col0 = g * L.a_group_cols;
+            const int a_row0 = g * L.a_group_rows + L.a_row_bias + L.off_min;
             for (int cb = 0; cb < L.cblocks; ++cb) {
                 if (DBG) t0 = clock64();
                 mbar_wait(&empty_s[slot], slot_phase ^ 1u);
@@ -135,10 +136,10 @@ conv_tc2_kernel(const __grid_constant__ GemmLayer L) {
                 if (elect_one()) {
                     uint8_t* sl = smem + slot * slab_slot_bytes;
                     if (leader) mbar_arrive_expect_tx(&full_s[slot], 2u * (uint32_t)slab_slot_bytes);
-                    tma_load_2d_pair(&L.tm_a_hi, &full_s[slot], sl, a_col0 + cb * BLOCK_K, m0 + L.off_min);
+                    tma_load_2d_pair(&L.tm_a_hi, &full_s[slot], sl, a_col0 + cb * BLOCK_K, m0 + a_row0);
                     if (A_LO)
                         tma_load_2d_pair(&L.tm_a_lo, &full_s[slot], sl + slab_plane, a_col0 + cb * BLOCK_K,
-                                         m0 + L.off_min);
+                                         m0 + a_row0);
                 }
                 __syncwarp();
                 if (++slot == L.n_slab_slots) { slot = 0; slot_phase ^= 1u; }
@@ -193,8 +194,10 @@ conv_tc2_kernel(const __grid_constant__ GemmLayer L) {
                             const uint32_t a_lo32 = a_hi32 + (uint32_t)(slab_plane >> 4);
                             const uint32_t b_hi32 = desc_lo(smem_u32(smem_b + stage * b_stage_bytes));
                             const uint32_t b_lo32 = b_hi32 + (uint32_t)(B_PLANE_BYTES >> 4);
+                            const int nk = (cb + 1 == L.cblocks) ? L.last_ksteps : BLOCK_K / UMMA_K;
 #pragma unroll
                             for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+                                if (k >= nk) break;
                                 const uint32_t ko = (uint32_t)(k * UMMA_K * 2 / 16);
                                 const uint32_t accum = (in_chunk > 0 || k > 0) ? 1u : 0u;
                                 umma_f16_pair(tmem_d, make_desc(a_hi32 + ko), make_desc(b_hi32 + ko), idesc, accum);

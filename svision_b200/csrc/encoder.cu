@@ -13,8 +13,8 @@
 //      floor((2*dy*i + dx - 1) / (2*dx))), so the pixels are drawn in parallel with atomicOr;
 //   3. channel 1 = channel 0 AND (columns holding >= 2 pixels): a carry-save "ones/twos"
 //      reduction over the rows, 32 columns per word;
-//   4. the CTA streams the image to HBM with 16-byte coalesced stores.  Background vectors (98 %
-//      of them) take a fast path: no per-element work.
+//   4. the CTA streams the image to HBM: a branch-free pass of 16-byte coalesced stores of the
+//      background pattern, then one scalar store per lit channel-pixel (see write_nhwc).
 // Output layouts: NHWC fp32 (what the reference materialises), NHWC fp16 (same values, lossless)
 // and the conv1 operand layout used by the fused path: space-to-depth 4x4 -> [57*57][64] fp16
 // (48 real channels (dy*4+dx)*3+c, 16 zero), see gemm layouts in DESIGN.md.
@@ -101,38 +101,65 @@ __device__ __forceinline__ uint4 nhwc_vector(int ph, uint32_t L) {
     return out;
 }
 
+// The image is > 98 % background, so it is written in two passes: (1) a branch-free stream of
+// 16-byte vectors holding the periodic background pattern (period 3 elements), (2) after a CTA
+// barrier, one scalar store per lit channel-pixel (~160 per image), which merges in L2 with the
+// line written microseconds earlier.  The stream loop is ~12 instructions per 512-byte warp
+// store; the first version decided lit/background per vector (~120 instructions) and was
+// instruction-bound at 27-50 % of the HBM roofline.
+template <typename T>
+__device__ __forceinline__ T level_value(int ch, bool lit) {
+    if constexpr (sizeof(T) == 4) return Levels<float>::get(ch, lit);
+    else return __ushort_as_half((unsigned short)Levels<__half>::get(ch, lit));
+}
+
 template <typename T>
 __device__ void write_nhwc(const uint32_t* bm, T* __restrict__ out_all, long long img) {
-    constexpr int EPV = 16 / (int)sizeof(T);
+    constexpr int EPV = 16 / (int)sizeof(T);                    // elements per 16-byte vector
     const int tid = threadIdx.x;
     const long long e_begin = img * (long long)NEL;
     const long long e_end = e_begin + NEL;
-    const long long v_first = (e_begin + EPV - 1) / EPV;
+    // the vector stream starts on a 128-byte line so every 512-byte warp store is 4 whole lines
+    constexpr int EPL = 128 / (int)sizeof(T);                   // elements per cache line
+    const long long v_first = ((e_begin + EPL - 1) / EPL) * (EPL / EPV);
     const long long v_last = e_end / EPV;                       // exclusive
-    const int head = (int)(v_first * EPV - e_begin);
+    const int head = (int)(v_first * EPV - e_begin);            // < EPL <= 64 scalar elements
     const int tail = (int)(e_end - v_last * EPV);
-    if (tid < head) out_all[e_begin + tid] = scalar_value<T>(bm, tid);
-    if (tid >= 32 && tid < 32 + tail) {
-        const int e = NEL - tail + (tid - 32);
-        out_all[e_begin + e] = scalar_value<T>(bm, e);
-    }
-    uint4* __restrict__ outv = reinterpret_cast<uint4*>(out_all);
     const int nvec = (int)(v_last - v_first);
+
+    // ---- pass 1: background everywhere ----
+    if (tid < head) out_all[e_begin + tid] = level_value<T>(tid % 3, false);
+    if (tid >= 64 && tid < 64 + tail) {
+        const int e = NEL - tail + (tid - 64);
+        out_all[e_begin + e] = level_value<T>(e % 3, false);
+    }
+    const uint4 bg0 = nhwc_vector<T>(0, 0u), bg1 = nhwc_vector<T>(1, 0u), bg2 = nhwc_vector<T>(2, 0u);
+    constexpr int DPH = (ENC_THREADS * EPV) % 3;                // phase step of the thread's stride
+    uint4* __restrict__ outv = reinterpret_cast<uint4*>(out_all) + v_first;
+    int ph = (head + tid * EPV) % 3;
+#pragma unroll 4
     for (int i = tid; i < nvec; i += ENC_THREADS) {
-        const int e = head + i * EPV;
-        const int p0 = e / 3, ph = e - 3 * p0;
-        const int r = p0 / IMG, c = p0 - r * IMG;
-        const uint32_t w0 = window4(bm, r, c);
-        const uint32_t w1 = window4(bm + PLANE, r, c);
-        const uint32_t w2 = window4(bm + 2 * PLANE, r, c);
-        uint32_t L = 0;
-        if (w0 | w2) {                                          // ch1 is a subset of ch0
-#pragma unroll
-            for (int px = 0; px < 4; ++px)
-                L |= (((w0 >> px) & 1u) | (((w1 >> px) & 1u) << 1) | (((w2 >> px) & 1u) << 2))
-                     << (3 * px);
+        outv[i] = ph == 0 ? bg0 : (ph == 1 ? bg1 : bg2);
+        ph += DPH;
+        if (ph >= 3) ph -= 3;
+    }
+    __syncthreads();                                            // background lands before the patches
+
+    // ---- pass 2: lit pixels (channel 0 plane drives; channels 1 and 2 are subsets of it) ----
+    T* __restrict__ o = out_all + e_begin;
+    for (int w = tid; w < IMG * BMW; w += ENC_THREADS) {
+        uint32_t bits = bm[w];
+        if (!bits) continue;
+        const uint32_t b1 = bm[PLANE + w], b2 = bm[2 * PLANE + w];
+        const int r = w >> 3, cbase = (w & 7) << 5;
+        while (bits) {
+            const int k = __ffs(bits) - 1;
+            bits &= bits - 1;
+            const int e = 3 * (r * IMG + cbase + k);
+            o[e] = level_value<T>(0, true);
+            if ((b1 >> k) & 1u) o[e + 1] = level_value<T>(1, true);
+            if ((b2 >> k) & 1u) o[e + 2] = level_value<T>(2, true);
         }
-        outv[v_first + i] = nhwc_vector<T>(ph, L);
     }
 }
 
@@ -186,17 +213,29 @@ __device__ void write_s2d(const uint32_t* bm, __half* __restrict__ out_all, long
 }
 
 template <int MODE>   // 0: NHWC f32, 1: NHWC f16, 2: conv1 operand (s2d f16)
-__global__ void __launch_bounds__(ENC_THREADS)
+__global__ void __launch_bounds__(ENC_THREADS, 8)
 encode_kernel(const int32_t* __restrict__ rows, long long n, void* __restrict__ out) {
     __shared__ __align__(16) uint32_t bm[3 * PLANE];
     __shared__ LineParams lines[2];
     __shared__ uint32_t red[(ENC_THREADS / 32) * 8 * 2];
     __shared__ uint32_t colmask[8];
+    // The 48-byte row of the NEXT image is fetched while the current image streams out: a global
+    // load issued behind a saturated store queue takes microseconds, and the line set-up (and with
+    // it the whole CTA, at the barrier) would otherwise wait for it on every image.
+    __shared__ int32_t rowbuf[2][12];
+    if (threadIdx.x < 12 && blockIdx.x < n) rowbuf[0][threadIdx.x] = rows[(long long)blockIdx.x * 12 + threadIdx.x];
+    __syncthreads();
+    int cur = 0;
     for (long long img = blockIdx.x; img < n; img += gridDim.x) {
-        build_bitmap(rows + img * 12, bm, lines, red, colmask);
+        const long long nxt = img + gridDim.x;
+        int32_t pre = 0;
+        if (threadIdx.x < 12 && nxt < n) pre = __ldg(rows + nxt * 12 + threadIdx.x);
+        build_bitmap<ENC_THREADS>(rowbuf[cur], bm, lines, red, colmask);
         if constexpr (MODE == 0) write_nhwc<float>(bm, reinterpret_cast<float*>(out), img);
         if constexpr (MODE == 1) write_nhwc<__half>(bm, reinterpret_cast<__half*>(out), img);
         if constexpr (MODE == 2) write_s2d(bm, reinterpret_cast<__half*>(out), img);
+        if (threadIdx.x < 12) rowbuf[cur ^ 1][threadIdx.x] = pre;
+        cur ^= 1;
         __syncthreads();
     }
 }
@@ -206,15 +245,26 @@ encode_kernel(const int32_t* __restrict__ rows, long long n, void* __restrict__ 
 int launch_encode(const int32_t* rows_dev, long long n, void* out, int mode, int num_sms,
                   cudaStream_t stream) {
     if (n <= 0) return 0;
-    // 22 KB smem + 256 threads per CTA -> 8 CTAs/SM resident; size the grid as a multiple of the
-    // SM count so the grid-stride loop has no ragged tail.
-    long long blocks = (long long)num_sms * 8;
+    if (mode < 0 || mode > 2) return fail(-1, "launch_encode: bad mode");
+    // One wave of resident CTAs, each looping over images: the grid is SMs x (CTAs that really fit
+    // per SM with the maximum shared-memory carveout), so the grid-stride loop has no ragged
+    // second wave (a fixed 8 x SMs grid ran as 1.6 waves: only 5 CTAs were resident).
+    static int blocks_per_sm[3] = {0, 0, 0};
+    if (blocks_per_sm[mode] == 0) {
+        const void* fn = mode == 0 ? (const void*)encode_kernel<0>
+                       : mode == 1 ? (const void*)encode_kernel<1> : (const void*)encode_kernel<2>;
+        cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+        int nb = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fn, ENC_THREADS, 0) != cudaSuccess || nb < 1)
+            nb = 4;
+        blocks_per_sm[mode] = nb;
+    }
+    long long blocks = (long long)num_sms * blocks_per_sm[mode];
     if (blocks > n) blocks = n;
     switch (mode) {
         case 0: encode_kernel<0><<<(unsigned)blocks, ENC_THREADS, 0, stream>>>(rows_dev, n, out); break;
         case 1: encode_kernel<1><<<(unsigned)blocks, ENC_THREADS, 0, stream>>>(rows_dev, n, out); break;
-        case 2: encode_kernel<2><<<(unsigned)blocks, ENC_THREADS, 0, stream>>>(rows_dev, n, out); break;
-        default: return fail(-1, "launch_encode: bad mode");
+        default: encode_kernel<2><<<(unsigned)blocks, ENC_THREADS, 0, stream>>>(rows_dev, n, out); break;
     }
     SVX_LAUNCH_CHECK("encode_kernel");
     return 0;

@@ -13,7 +13,8 @@ constexpr int NEL = NPIX * 3;            // 154587 elements per image
 constexpr int BMW = 8;                   // 32-bit words per bitmap row (256 >= 227 columns)
 constexpr int BMROWS = 228;              // +1 all-zero row (space-to-depth pad row / straddle reads)
 constexpr int PLANE = BMROWS * BMW;      // words per channel plane
-constexpr int ENC_THREADS = 256;
+constexpr int ENC_THREADS = 128;         // encoder: small CTAs, ~8 resident per SM hide the serial line set-up
+constexpr int FRONT_THREADS = 256;       // fused front end: more warps per site for the lit-pixel work
 
 struct LineParams {
     int x1, y1, dx, dy, sy, vert, count, rev;
@@ -93,18 +94,19 @@ static __device__ __forceinline__ LineParams setup_line(const int32_t* __restric
 }
 
 // Builds the three bit planes of one image in shared memory.  All threads of the CTA call it.
+template <int NT>
 static __device__ __forceinline__ void build_bitmap(const int32_t* __restrict__ row, uint32_t* bm, LineParams* lines,
-                             uint32_t* red /* [8 warps][8 words][2] */, uint32_t* colmask) {
+                             uint32_t* red /* [NT/32 warps][8 words][2] */, uint32_t* colmask) {
     const int tid = threadIdx.x;
     // zero the planes (3*228*8 words = 1368 uint4)
     uint4* bz = reinterpret_cast<uint4*>(bm);
-    for (int i = tid; i < 3 * PLANE / 4; i += ENC_THREADS) bz[i] = make_uint4(0, 0, 0, 0);
+    for (int i = tid; i < 3 * PLANE / 4; i += NT) bz[i] = make_uint4(0, 0, 0, 0);
     if (tid < 2) lines[tid] = setup_line(row, tid);
     __syncthreads();
 #pragma unroll
     for (int s = 0; s < 2; ++s) {
         const LineParams L = lines[s];
-        for (int i = tid; i < L.count; i += ENC_THREADS) {
+        for (int i = tid; i < L.count; i += NT) {
             const int st = L.dx > 0 ? (2 * L.dy * i + L.dx - 1) / (2 * L.dx) : 0;
             const int c = L.vert ? L.x1 + st : L.x1 + i;
             const int r = L.vert ? L.y1 + L.sy * i : L.y1 + L.sy * st;
@@ -116,11 +118,13 @@ static __device__ __forceinline__ void build_bitmap(const int32_t* __restrict__ 
     __syncthreads();
     // columns with >= 2 lit pixels: per 32-column word, (ones, twos) carry-save over rows
     {
-        const int w = tid & 7, chunk = tid >> 3;           // 32 chunks of 8 rows (last: 3 rows)
+        constexpr int NCHUNK = NT / 8;            // row chunks; 4 of them per warp
+        constexpr int CROWS = (IMG + NCHUNK - 1) / NCHUNK;
+        const int w = tid & 7, chunk = tid >> 3;
         uint32_t ones = 0, twos = 0;
-        const int r0 = chunk * 8;
+        const int r0 = chunk * CROWS;
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
+        for (int k = 0; k < CROWS; ++k) {
             const int r = r0 + k;
             const uint32_t v = r < IMG ? bm[r * BMW + w] : 0u;
             twos |= ones & v;
@@ -142,7 +146,7 @@ static __device__ __forceinline__ void build_bitmap(const int32_t* __restrict__ 
     if (tid < 8) {
         uint32_t ones = 0, twos = 0;
 #pragma unroll
-        for (int q = 0; q < ENC_THREADS / 32; ++q) {
+        for (int q = 0; q < NT / 32; ++q) {
             const uint32_t o2 = red[(q * 8 + tid) * 2 + 0], t2 = red[(q * 8 + tid) * 2 + 1];
             twos |= t2 | (ones & o2);
             ones |= o2;
@@ -150,7 +154,7 @@ static __device__ __forceinline__ void build_bitmap(const int32_t* __restrict__ 
         colmask[tid] = twos;
     }
     __syncthreads();
-    for (int i = tid; i < IMG * BMW; i += ENC_THREADS)
+    for (int i = tid; i < IMG * BMW; i += NT)
         bm[PLANE + i] = bm[i] & colmask[i & 7];             // plot_segment.py:59-65
     __syncthreads();
 }

@@ -36,7 +36,6 @@ using namespace bitmap;
 constexpr int POOLED = 27;
 constexpr int NPOS = POOLED * POOLED;        // 729
 constexpr int G2W = 29, G2POS = G2W * G2W;   // conv2 operand grid (27 + 2 shared pad)
-constexpr int X2_LD = 128;                   // 2 groups x (48 real + 16 zero) channels
 
 // bits [c, c+19) of bitmap row r (c + 18 <= 226, so both words lie inside the row)
 __device__ __forceinline__ uint32_t window19(const uint32_t* plane, int r, int c) {
@@ -65,11 +64,11 @@ __device__ __forceinline__ void lrn3(const float (&m)[3], float (&out)[3], int l
     }
 }
 
-__global__ void __launch_bounds__(ENC_THREADS)
+__global__ void __launch_bounds__(FRONT_THREADS, 4)
 front_kernel(const int32_t* __restrict__ rows, long long n, const FrontParams P) {
     __shared__ __align__(16) uint32_t bm[3 * PLANE];
     __shared__ LineParams lines[2];
-    __shared__ uint32_t red[(ENC_THREADS / 32) * 8 * 2];
+    __shared__ uint32_t red[(FRONT_THREADS / 32) * 8 * 2];
     __shared__ uint32_t colmask[8];
     __shared__ __align__(16) unsigned short bg[2][96];     // background vector: hi plane, lo plane
     __shared__ uint32_t dirty_mask[(NPOS + 31) / 32];
@@ -93,13 +92,21 @@ front_kernel(const int32_t* __restrict__ rows, long long n, const FrontParams P)
         }
     }
 
+    // prefetch of the next site's row: see encode_kernel
+    __shared__ int32_t rowbuf[2][12];
+    if (tid < 12 && blockIdx.x < n) rowbuf[0][tid] = rows[(long long)blockIdx.x * 12 + tid];
+    __syncthreads();
+    int cur = 0;
     for (long long img = blockIdx.x; img < n; img += gridDim.x) {
+        const long long nxt = img + gridDim.x;
+        int32_t pre = 0;
+        if (tid < 12 && nxt < n) pre = __ldg(rows + nxt * 12 + tid);
         if (tid < (NPOS + 31) / 32) dirty_mask[tid] = 0;
         if (tid == 0) dirty_count = 0;
-        build_bitmap(rows + img * 12, bm, lines, red, colmask);      // ends with __syncthreads()
+        build_bitmap<FRONT_THREADS>(rowbuf[cur], bm, lines, red, colmask);          // ends with __syncthreads()
 
         // ---- which pooled positions see a lit pixel? (receptive field: rows/cols 8p .. 8p+18)
-        for (int p = tid; p < NPOS; p += ENC_THREADS) {
+        for (int p = tid; p < NPOS; p += FRONT_THREADS) {
             const int py = p / POOLED, px = p - py * POOLED;
             uint32_t any = 0;
 #pragma unroll
@@ -114,7 +121,7 @@ front_kernel(const int32_t* __restrict__ rows, long long n, const FrontParams P)
         // ---- background positions: 12 channel octets x 2 planes per position, 16-byte stores
         __half* const planes[2] = {P.x2_hi, P.x2_lo};
         const long long img_row0 = img * G2POS;
-        for (int v = tid; v < NPOS * 24; v += ENC_THREADS) {
+        for (int v = tid; v < NPOS * 24; v += FRONT_THREADS) {
             const int plane = v >= NPOS * 12;
             const int rem = v - plane * NPOS * 12;
             const int p = rem / 12, o = rem - p * 12;
@@ -122,13 +129,13 @@ front_kernel(const int32_t* __restrict__ rows, long long n, const FrontParams P)
             const int py = p / POOLED, px = p - py * POOLED;
             const uint4 val = *reinterpret_cast<const uint4*>(&bg[plane][8 * o]);
             const long long off =
-                (img_row0 + py * G2W + px) * X2_LD + (o / 6) * 64 + (o % 6) * 8;
+                (long long)(o / 6) * P.group_elems + (img_row0 + py * G2W + px) * P.ld + (o % 6) * 8;
             *reinterpret_cast<uint4*>(planes[plane] + off) = val;
         }
 
         // ---- flagged positions: one warp each
         const int nd = dirty_count;
-        for (int i = warp; i < nd; i += ENC_THREADS / 32) {
+        for (int i = warp; i < nd; i += FRONT_THREADS / 32) {
             const int p = dirty_list[i];
             const int py = p / POOLED, px = p - py * POOLED;
             const int r0 = 8 * py, c0 = 8 * px;
@@ -172,7 +179,7 @@ front_kernel(const int32_t* __restrict__ rows, long long n, const FrontParams P)
                 for (int j = 0; j < 3; ++j) m[j] = fmaxf(m[j], acc[q][j]);
             lrn3(m, o, lane);
             const long long off =
-                (img_row0 + py * G2W + px) * X2_LD + (c3 / 48) * 64 + (c3 % 48);
+                (long long)(c3 / 48) * P.group_elems + (img_row0 + py * G2W + px) * P.ld + (c3 % 48);
 #pragma unroll
             for (int j = 0; j < 3; ++j) {
                 const __half h = __float2half_rn(o[j]);
@@ -180,6 +187,8 @@ front_kernel(const int32_t* __restrict__ rows, long long n, const FrontParams P)
                 P.x2_lo[off + j] = __float2half_rn(o[j] - __half2float(h));
             }
         }
+        if (tid < 12) rowbuf[cur ^ 1][tid] = pre;
+        cur ^= 1;
         __syncthreads();
     }
 }
@@ -189,9 +198,20 @@ front_kernel(const int32_t* __restrict__ rows, long long n, const FrontParams P)
 int launch_front(const int32_t* rows_dev, long long n, const FrontParams& P, int num_sms,
                  cudaStream_t stream) {
     if (n <= 0) return 0;
-    long long blocks = (long long)num_sms * 6;
+    static int blocks_per_sm = 0;                 // one wave of resident CTAs (see launch_encode)
+    if (blocks_per_sm == 0) {
+        cudaFuncSetAttribute(front_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+        int nb = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, front_kernel, bitmap::FRONT_THREADS, 0) !=
+                cudaSuccess || nb < 1)
+            nb = 4;
+        blocks_per_sm = nb;
+    }
+    // per-site work varies with the number of lit pixels: oversubscribe (8 waves) so that the
+    // block scheduler balances the load instead of a static stride over one resident wave
+    long long blocks = (long long)num_sms * blocks_per_sm * 8;
     if (blocks > n) blocks = n;
-    front_kernel<<<(unsigned)blocks, bitmap::ENC_THREADS, 0, stream>>>(rows_dev, n, P);
+    front_kernel<<<(unsigned)blocks, bitmap::FRONT_THREADS, 0, stream>>>(rows_dev, n, P);
     SVX_LAUNCH_CHECK("front_kernel");
     return 0;
 }

@@ -17,8 +17,10 @@ int launch_encode(const int32_t* rows_dev, long long n, void* out, int mode, int
 struct FrontParams {
     const float* w255;         // [11][11][3][96] = 255 * conv1 weights (TF layout)
     const float* base;         // [96] = bias + sum_k lo_ch * W[k]  (conv1 of the all-background image)
-    __half* x2_hi;             // conv2 operand [n*841][128], see DESIGN.md §3
+    __half* x2_hi;             // conv2 operand, see DESIGN.md §3
     __half* x2_lo;
+    int ld;                    // elements per position row (128 padded layout, 48 packed layout)
+    long long group_elems;     // element offset of channel group 1 (64 padded, plane size packed)
 };
 int launch_front(const int32_t* rows_dev, long long n, const FrontParams& P, int num_sms,
                  cudaStream_t stream);
@@ -40,6 +42,11 @@ struct GemmLayer {
     int taps;                  // filter taps (1 for fc)
     int cblocks;               // 64-wide channel blocks per tap
     int a_group_cols;          // column offset of group g in A
+    int a_group_rows;          // row offset of group g in A (group-major planes); usually 0
+    int a_row_bias;            // constant added to every A row coordinate (leading zero rows of the
+                               // buffer, so overlapping-row maps never see a negative row)
+    int last_ksteps;           // 16-wide k-steps issued in the LAST channel block of a tap (1..4):
+                               // lets a tap's K be any multiple of 16 (zero tail never multiplied)
     int row_off[GEMM_MAX_TAPS];
     int use_a_lo, use_b_lo;    // which hi/lo cross terms are issued (3-pass / 2-pass / 1-pass)
     long long m_rows;          // rows of D actually computed (and of A addressable)
@@ -92,7 +99,9 @@ struct PoolParams {
     __half* out_lo;
     int out_ld;                // leading dimension of the output rows (elements)
     int out_grid_w, out_pos_per_img;   // output row = img*out_pos_per_img + y*out_grid_w + x
-    int group_real, group_pad; // output column of channel c = (c / group_real)*group_pad + c % group_real
+    int group_real;            // channels per output group
+    long long group_elems;     // element offset between groups: channel c of row r lives at
+                               //   (c / group_real) * group_elems + r * out_ld + c % group_real
     int flatten;               // 1: output is [n][out_h*out_w*C] (NHWC flatten for fc6)
 };
 int launch_pool(const PoolParams& p, long long n_img, int num_sms, cudaStream_t stream);

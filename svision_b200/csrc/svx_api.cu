@@ -61,6 +61,9 @@ struct svx_handle {
     bool use_front = true;               // fused sparse front end (front.cu) in the classify path
     float* front_w255 = nullptr;
     float* front_base = nullptr;
+    bool use_pack = true;                // conv2 K-packing: 48-channel positions, 5 row-taps x 240 (K = 1200)
+    long long x2_group_elems = 64;       // element offset of channel group 1 in x2
+    int x2_ld = 128;                     // elements per x2 position row
     bool use_pair = true;                // conv_tc2.cu (cta_group::2) where the layer supports it
     bool use_slab = true;                // conv_tc.cu (A halo slab) vs gemm_tc.cu (A tile per tap)
     int desc_bo_mode = 0;                // measured on B200: swizzle uses absolute smem address bits, so
@@ -133,9 +136,16 @@ int dev_alloc(svx_handle* h, T** p, size_t count, bool zero = true) {
 }
 
 // TF-layout weights -> K-major [n_total][taps*cg_pad] fp16 hi/lo planes on the device.
+// K layout of the packed conv2: [kh][kw*48 + c] with each kernel row padded 240 -> 256
+constexpr int kPackTaps = 5, kPackK = 256;
+// zero rows in front of the packed x2: a virtual (overlapping) row with a NEGATIVE index would be
+// zero-filled by TMA as a whole although most of its 256 elements are valid data
+constexpr int kPackLeadRows = 64;
+
 int upload_layer_weights(svx_handle* h, int li, const float* w_tf, const float* b_tf) {
     const LayerSpec& s = kSpec[li];
-    const size_t K = (size_t)s.taps * s.cg_pad;
+    const bool packed = li == L_CONV2 && h->use_pack;
+    const size_t K = packed ? (size_t)kPackTaps * kPackK : (size_t)s.taps * s.cg_pad;
     const size_t count = (size_t)s.n_total * K;
     std::vector<__half> hi(count), lo(count);
     std::memset(hi.data(), 0, count * sizeof(__half));
@@ -159,6 +169,13 @@ int upload_layer_weights(svx_handle* h, int li, const float* w_tf, const float* 
                                 put(n, (size_t)(a * 3 + b) * 64 + (dy * 4 + dx) * 3 + c,
                                     w_tf[((size_t)(kh * 11 + kw) * 3 + c) * 96 + n]);
                     }
+    } else if (packed) {
+        for (int kh = 0; kh < 5; ++kh)
+            for (int kw = 0; kw < 5; ++kw)
+                for (int c = 0; c < 48; ++c) {
+                    const float* src = w_tf + ((size_t)(kh * 5 + kw) * 48 + c) * s.n_total;
+                    for (int n = 0; n < s.n_total; ++n) put(n, (size_t)kh * kPackK + kw * 48 + c, src[n]);
+                }
     } else {
         for (int t = 0; t < s.taps; ++t)
             for (int c = 0; c < s.cg_real; ++c) {
@@ -182,7 +199,8 @@ int setup_layer(svx_handle* h, int li, const __half* a_hi, const __half* a_lo, l
     const LayerSpec& s = kSpec[li];
     GemmLayer& L = h->layer[li];
     std::memset(&L, 0, sizeof(L));
-    const long long K = (long long)s.taps * s.cg_pad;
+    const bool packed = li == L_CONV2 && h->use_pack;
+    const long long K = packed ? (long long)kPackTaps * kPackK : (long long)s.taps * s.cg_pad;
     int rc;
     L.block_n = s.block_n;
     L.chunk_kblocks = kChunkKBlocks;
@@ -191,9 +209,28 @@ int setup_layer(svx_handle* h, int li, const __half* a_hi, const __half* a_lo, l
     L.taps = s.taps;
     L.cblocks = s.cg_pad / GEMM_BLOCK_K;
     L.a_group_cols = s.cg_pad;
+    L.a_group_rows = 0;
+    L.last_ksteps = GEMM_BLOCK_K / 16;
     for (int kh = 0; kh < s.kh; ++kh)
         for (int kw = 0; kw < s.kw; ++kw)
             L.row_off[kh * s.kw + kw] = (kh - center) * grid_w + (kw - center);
+    long long a_cols = lda;                       // logical row length seen by the A tensor maps
+    if (packed) {
+        // one tap per kernel ROW: its 5 x 48 = 240 operand values are contiguous in the packed x2
+        // (row stride 48 elements), read as 4 K-blocks through overlapping-row tensor maps; the
+        // last block issues 3 of its 4 k-steps (240 = 15 x 16)
+        L.taps = kPackTaps;
+        L.cblocks = kPackK / GEMM_BLOCK_K;
+        L.last_ksteps = 3;
+        L.a_group_cols = 0;
+        L.a_group_rows = (int)(h->x2_group_elems / 48);
+        for (int kh = 0; kh < 5; ++kh) L.row_off[kh] = (kh - 2) * grid_w - 2;
+        a_cols = kPackK;
+        a_rows = kPackLeadRows + 2 * (h->x2_group_elems / 48);
+        L.a_row_bias = kPackLeadRows;
+        a_hi -= (size_t)kPackLeadRows * 48;       // tensor maps start at the leading zero rows
+        a_lo -= (size_t)kPackLeadRows * 48;
+    }
     const bool three = h->precision == SVX_PRECISION_3PASS;
     L.use_b_lo = three ? 1 : 0;
     L.use_a_lo = (three && a_lo != nullptr) ? 1 : 0;
@@ -220,8 +257,8 @@ int setup_layer(svx_handle* h, int li, const __half* a_hi, const __half* a_lo, l
         L.desc_base_offset_mode = h->desc_bo_mode;
         a_box_rows = L.slab_rows;
     }
-    if ((rc = make_tensor_map_2d(&L.tm_a_hi, a_hi, a_rows, lda, lda, a_box_rows))) return rc;
-    if ((rc = make_tensor_map_2d(&L.tm_a_lo, a_lo ? a_lo : a_hi, a_rows, lda, lda, a_box_rows))) return rc;
+    if ((rc = make_tensor_map_2d(&L.tm_a_hi, a_hi, a_rows, a_cols, lda, a_box_rows))) return rc;
+    if ((rc = make_tensor_map_2d(&L.tm_a_lo, a_lo ? a_lo : a_hi, a_rows, a_cols, lda, a_box_rows))) return rc;
     if ((rc = make_tensor_map_2d(&L.tm_b_hi, h->w_hi[li], s.n_total, K, K, b_box_rows))) return rc;
     if ((rc = make_tensor_map_2d(&L.tm_b_lo, h->w_lo[li], s.n_total, K, K, b_box_rows))) return rc;
     return 0;
@@ -267,8 +304,20 @@ int build_model(svx_handle* h, const svx_weights* w) {
 
     // activations: zero once; pad positions/channels are never written afterwards
     if ((rc = dev_alloc(h, &h->y1, (size_t)B * P1 * 96))) return rc;
-    if ((rc = dev_alloc(h, &h->x2_hi, (size_t)B * P2 * 128))) return rc;
-    if ((rc = dev_alloc(h, &h->x2_lo, (size_t)B * P2 * 128))) return rc;
+    size_t x2_elems = (size_t)B * P2 * 128;
+    if (h->use_pack) {
+        // packed: two group planes of [B*841 + 64 zero rows][48]; the zero rows are the top padding
+        // of the next plane and absorb the 256-wide over-read of the last positions
+        h->x2_ld = 48;
+        h->x2_group_elems = ((long long)B * P2 + 64) * 48;
+        x2_elems = (size_t)(kPackLeadRows * 48 + 2 * h->x2_group_elems + 256);
+    }
+    if ((rc = dev_alloc(h, &h->x2_hi, x2_elems))) return rc;
+    if ((rc = dev_alloc(h, &h->x2_lo, x2_elems))) return rc;
+    if (h->use_pack) {                           // data pointers start after the leading zero rows
+        h->x2_hi += (size_t)kPackLeadRows * 48;
+        h->x2_lo += (size_t)kPackLeadRows * 48;
+    }
     if ((rc = dev_alloc(h, &h->y2, (size_t)B * P2 * 256))) return rc;
     if ((rc = dev_alloc(h, &h->x3_hi, (size_t)B * P3 * 256))) return rc;
     if ((rc = dev_alloc(h, &h->x3_lo, (size_t)B * P3 * 256))) return rc;
@@ -286,7 +335,7 @@ int build_model(svx_handle* h, const svx_weights* w) {
 
     //                 layer    A hi      A lo      A rows  lda grid center out_f32 out_hi    out_lo   ldc  pos  vh  vw
     if ((rc = setup_layer(h, L_CONV1, h->x1, nullptr, B * P1, 64, S2D, 0, h->y1, nullptr, nullptr, 96, 0, 0, 0))) return rc;
-    if ((rc = setup_layer(h, L_CONV2, h->x2_hi, h->x2_lo, B * P2, 128, G2, 2, h->y2, nullptr, nullptr, 256, 0, 0, 0))) return rc;
+    if ((rc = setup_layer(h, L_CONV2, h->x2_hi, h->x2_lo, B * P2, h->x2_ld, G2, 2, h->y2, nullptr, nullptr, 256, 0, 0, 0))) return rc;
     if ((rc = setup_layer(h, L_CONV3, h->x3_hi, h->x3_lo, B * P3, 256, G3, 1, nullptr, h->x4_hi, h->x4_lo, 384, P3, 13, 13))) return rc;
     if ((rc = setup_layer(h, L_CONV4, h->x4_hi, h->x4_lo, B * P3, 384, G3, 1, nullptr, h->x5_hi, h->x5_lo, 384, P3, 13, 13))) return rc;
     if ((rc = setup_layer(h, L_CONV5, h->x5_hi, h->x5_lo, B * P3, 384, G3, 1, h->y5, nullptr, nullptr, 256, 0, 0, 0))) return rc;
@@ -342,8 +391,8 @@ int run_cnn(svx_handle* h, long long n, int32_t* labels, float* probs, float* lo
     if ((rc = run_layer(h, L_CONV1, st))) return rc;
     PoolParams p1{};
     p1.in = h->y1; p1.in_grid_w = S2D; p1.in_pos_per_img = P1; p1.C = 96; p1.out_h = 27; p1.out_w = 27;
-    p1.lrn = 1; p1.out_hi = h->x2_hi; p1.out_lo = h->x2_lo; p1.out_ld = 128; p1.out_grid_w = G2;
-    p1.out_pos_per_img = P2; p1.group_real = 48; p1.group_pad = 64; p1.flatten = 0;
+    p1.lrn = 1; p1.out_hi = h->x2_hi; p1.out_lo = h->x2_lo; p1.out_ld = h->x2_ld; p1.out_grid_w = G2;
+    p1.out_pos_per_img = P2; p1.group_real = 48; p1.group_elems = h->x2_group_elems; p1.flatten = 0;
     mark(h, 2, st);
     if ((rc = launch_pool(p1, n, h->num_sms, st))) return rc;
     }
@@ -353,7 +402,7 @@ int run_cnn(svx_handle* h, long long n, int32_t* labels, float* probs, float* lo
     PoolParams p2{};
     p2.in = h->y2; p2.in_grid_w = G2; p2.in_pos_per_img = P2; p2.C = 256; p2.out_h = 13; p2.out_w = 13;
     p2.lrn = 1; p2.out_hi = h->x3_hi; p2.out_lo = h->x3_lo; p2.out_ld = 256; p2.out_grid_w = G3;
-    p2.out_pos_per_img = P3; p2.group_real = 256; p2.group_pad = 256; p2.flatten = 0;
+    p2.out_pos_per_img = P3; p2.group_real = 256; p2.group_elems = 256; p2.flatten = 0;
     mark(h, 4, st);
     if ((rc = launch_pool(p2, n, h->num_sms, st))) return rc;
 
@@ -366,7 +415,7 @@ int run_cnn(svx_handle* h, long long n, int32_t* labels, float* probs, float* lo
     PoolParams p5{};
     p5.in = h->y5; p5.in_grid_w = G3; p5.in_pos_per_img = P3; p5.C = 256; p5.out_h = 6; p5.out_w = 6;
     p5.lrn = 0; p5.out_hi = h->x6_hi; p5.out_lo = h->x6_lo; p5.out_ld = 9216; p5.out_grid_w = 6;
-    p5.out_pos_per_img = 36; p5.group_real = 256; p5.group_pad = 256; p5.flatten = 1;
+    p5.out_pos_per_img = 36; p5.group_real = 256; p5.group_elems = 256; p5.flatten = 1;
     mark(h, 8, st);
     if ((rc = launch_pool(p5, n, h->num_sms, st))) return rc;
 
@@ -384,7 +433,7 @@ int run_cnn(svx_handle* h, long long n, int32_t* labels, float* probs, float* lo
 // rows -> conv2 operand (fused sparse front end) or rows -> conv1 operand (dense path)
 int encode_front(svx_handle* h, const int32_t* rows_dev, long long m, cudaStream_t st) {
     if (h->use_front) {
-        FrontParams fp{h->front_w255, h->front_base, h->x2_hi, h->x2_lo};
+        FrontParams fp{h->front_w255, h->front_base, h->x2_hi, h->x2_lo, h->x2_ld, h->x2_group_elems};
         return launch_front(rows_dev, m, fp, h->num_sms, st);
     }
     return launch_encode(rows_dev, m, h->x1, 2, h->num_sms, st);
@@ -423,6 +472,8 @@ int svx_create(const svx_weights* weights, int device, int64_t max_batch, int pr
     if (const char* e = std::getenv("SVX_SLAB")) h->use_slab = std::atoi(e) != 0;
     if (const char* e = std::getenv("SVX_FRONT")) h->use_front = std::atoi(e) != 0;
     if (const char* e = std::getenv("SVX_PAIR")) h->use_pair = std::atoi(e) != 0;
+    if (const char* e = std::getenv("SVX_PACK")) h->use_pack = std::atoi(e) != 0;
+    if (!h->use_slab) h->use_pack = false;            // the per-tap kernel has no partial k-blocks
     if (const char* e = std::getenv("SVX_DESC_BO")) h->desc_bo_mode = std::atoi(e);
     h->num_sms = prop.multiProcessorCount;
     h->max_batch = max_batch;
@@ -565,10 +616,10 @@ int svx_debug_activation(svx_handle* h, const char* name, int64_t n, float* out_
     if (n <= 0 || n > h->last_n) return fail(SVX_ERR_INVALID, "svx_debug_activation: n exceeds the last micro-batch");
     DeviceGuard guard(h->device);
     SVX_CUDA_CHECK(cudaDeviceSynchronize());
-    struct Src { const char* name; const float* f32; const __half* hi; const __half* lo; int pos, grid_w, H, W, ld, C, greal, gpad; };
+    struct Src { const char* name; const float* f32; const __half* hi; const __half* lo; int pos, grid_w, H, W, ld, C, greal; long long gelems; };
     const Src table[] = {
         {"conv1", h->y1, nullptr, nullptr, P1, S2D, 55, 55, 96, 96, 96, 96},
-        {"norm1", nullptr, h->x2_hi, h->x2_lo, P2, G2, 27, 27, 128, 96, 48, 64},
+        {"norm1", nullptr, h->x2_hi, h->x2_lo, P2, G2, 27, 27, h->x2_ld, 96, 48, h->x2_group_elems},
         {"conv2", h->y2, nullptr, nullptr, P2, G2, 27, 27, 256, 256, 256, 256},
         {"norm2", nullptr, h->x3_hi, h->x3_lo, P3, G3, 13, 13, 256, 256, 256, 256},
         {"conv3", nullptr, h->x4_hi, h->x4_lo, P3, G3, 13, 13, 384, 384, 384, 384},
@@ -580,7 +631,8 @@ int svx_debug_activation(svx_handle* h, const char* name, int64_t n, float* out_
     };
     for (const Src& s : table) {
         if (std::strcmp(s.name, name) != 0) continue;
-        const size_t count = (size_t)n * s.pos * s.ld;
+        const int ngroups = s.C / s.greal;
+        const size_t count = (size_t)(ngroups - 1) * (size_t)s.gelems + ((size_t)n * s.pos - 1) * s.ld + s.greal;
         std::vector<float> buf(count);
         if (s.f32) {
             SVX_CUDA_CHECK(cudaMemcpy(buf.data(), s.f32, count * sizeof(float), cudaMemcpyDeviceToHost));
@@ -595,8 +647,8 @@ int svx_debug_activation(svx_handle* h, const char* name, int64_t n, float* out_
             for (int y = 0; y < s.H; ++y)
                 for (int x = 0; x < s.W; ++x)
                     for (int c = 0; c < s.C; ++c) {
-                        const int col = (c / s.greal) * s.gpad + (c % s.greal);
-                        out_host[o++] = buf[((size_t)im * s.pos + (size_t)y * s.grid_w + x) * s.ld + col];
+                        out_host[o++] = buf[(size_t)(c / s.greal) * (size_t)s.gelems +
+                                            ((size_t)im * s.pos + (size_t)y * s.grid_w + x) * s.ld + (c % s.greal)];
                     }
         return SVX_OK;
     }
