@@ -43,6 +43,9 @@ MICRO_BATCH = 2048
 CNN_FLOP_PER_SITE = 1_440_662_592            # SURVEY.md §8(a) layer table (2 x 720 331 296 MACs)
 FC8_FLOP_PER_SITE = 2 * 20_480               # runs on CUDA cores, not in the tensor-core kernel
 ENC_BYTES_PER_SITE = 48 + 227 * 227 * 3 * 2  # 16-bit image is what is emitted
+# dram__bytes_read.sum + dram__bytes_write.sum of the conv2 launch (2048 sites) from the committed
+# `ncu --set full` capture profiles/r1d_ncu_full_summary.txt: 662.8 MB + 1711 MB
+CONV2_DRAM_BYTES_PER_SITE = (662.823e6 + 1.711e9) / 2048
 #: algorithmic FLOPs per site of each tensor-core layer (groups honoured, no padding credit)
 LAYER_FLOP = {"conv1": 2 * 105_415_200, "conv2": 2 * 223_948_800, "conv3": 2 * 149_520_384,
               "conv4": 2 * 112_140_288, "conv5": 2 * 74_760_192, "fc6": 2 * 37_748_736,
@@ -329,12 +332,24 @@ def run_gpu(args):
                     "d2h_bytes_per_step": int(n * world * 24)},
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "roofline": {"kernel": "conv_tc2_kernel (tcgen05 cta_group::2 layer kernel: " + ", ".join(gemm_slots) + ")",
-                         "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                         "frac": achieved / peak if peak else None, "traffic": None,
+            # dominant kernel = the conv2 launch of the tensor-core layer kernel (largest single launch)
+            "roofline": {"kernel": "conv_tc2_kernel<128,3> (tcgen05 cta_group::2 layer kernel), conv2 launch",
+                         "bound": "tensor",
+                         "achieved": layers["conv2"].get("tflops_algorithmic", 0.0), "peak": peak,
+                         "unit": "TFLOP/s",
+                         "frac": layers["conv2"].get("tflops_algorithmic", 0.0) / peak if peak else None,
+                         "traffic": CONV2_DRAM_BYTES_PER_SITE * sites_rank / max(prof["conv2"][1], 1),
+                         "traffic_note": "bytes per launch, from ncu dram__bytes_read.sum + "
+                                         "dram__bytes_write.sum (profiles/r1d_ncu_full_summary.txt) scaled to "
+                                         "this run's sites per launch; algorithmic bytes are the same "
+                                         "(x2 operand read once, y2 written once)",
+                         "ms_per_launch": layers["conv2"]["ms_per_launch"],
+                         "share_of_step": prof["conv2"][0] / ms_total if ms_total > 0 else None,
                          "peak_source": peaks["source"] + ", bf16 sustained",
-                         "launches": gemm_launches,
-                         "share_of_step": gemm_ms / ms_total if ms_total > 0 else None,
+                         "all_tensor_layers": {"layers": list(gemm_slots), "achieved": achieved,
+                                               "frac": achieved / peak if peak else None,
+                                               "launches": gemm_launches,
+                                               "share_of_step": gemm_ms / ms_total if ms_total > 0 else None},
                          "algorithmic_gflop_per_site": sum(LAYER_FLOP[k] for k in gemm_slots) / 1e9,
                          "note": "3-pass fp16-split parity recipe executes 3x the algorithmic FLOPs plus "
                                  "layout padding (conv2 channels 48->64, padded grids); frac counts "
