@@ -17,10 +17,14 @@
 // images (svx_forward) and the parity tests cross-check the two.
 //
 // One CTA per site: bitmap in shared memory (encoder_bitmap.cuh, bit-exact with the reference
-// rasteriser); threads flag the pooled positions whose 19x19 receptive field holds a lit pixel;
-// background positions are streamed out with 16-byte stores; one warp per flagged position
-// walks the lit pixels of its field, lane = 3 consecutive output channels (weight reads are
-// coalesced over n), then max-pool, LRN by shuffle, fp16 hi/lo split.
+// rasteriser); the lit pixels mark the conv1 positions whose 11x11 window they fall in (~350 of
+// 3 025) and those mark the pooled positions that see them (~140 of 729).  Background pooled
+// positions are streamed out with 16-byte stores.  Phase A: one warp per dirty conv1 position
+// walks the lit pixels of its window once, lane = 3 consecutive output channels (weight reads are
+// coalesced over n), result to a per-CTA scratch that stays in L2.  Phase B: one warp per dirty
+// pooled position takes the max over its 3x3 conv positions (scratch value, or the background
+// value), ReLU, LRN by shuffle, fp16 hi/lo split.  (The first version recomputed every conv
+// position for each of the up to four pooled windows containing it.)
 #include "common.cuh"
 #include "encoder_bitmap.cuh"
 #include "kernels.h"
@@ -64,6 +68,16 @@ __device__ __forceinline__ void lrn3(const float (&m)[3], float (&out)[3], int l
     }
 }
 
+constexpr int CONV_W = 55, NCONV = CONV_W * CONV_W;      // conv1 output grid, 3025 positions
+constexpr unsigned short CLEAN = 0xFFFF;
+
+// bits [c, c+11) of bitmap row r (c + 10 <= 226)
+__device__ __forceinline__ uint32_t window11(const uint32_t* plane, int r, int c) {
+    const uint32_t* rowp = plane + r * BMW;
+    const int wi = c >> 5;
+    return __funnelshift_r(rowp[wi], rowp[wi + 1], c & 31) & 0x7FFu;
+}
+
 __global__ void __launch_bounds__(FRONT_THREADS, 4)
 front_kernel(const int32_t* __restrict__ rows, long long n, const FrontParams P) {
     __shared__ __align__(16) uint32_t bm[3 * PLANE];
@@ -71,18 +85,25 @@ front_kernel(const int32_t* __restrict__ rows, long long n, const FrontParams P)
     __shared__ uint32_t red[(FRONT_THREADS / 32) * 8 * 2];
     __shared__ uint32_t colmask[8];
     __shared__ __align__(16) unsigned short bg[2][96];     // background vector: hi plane, lo plane
+    __shared__ uint32_t cdirty[CONV_W * 2];                // dirty conv1 positions: 55 rows x 64 bits
+    __shared__ unsigned short cslot[NCONV];                // conv position -> scratch slot (CLEAN if none)
+    __shared__ unsigned short clist[NCONV];                // scratch slot -> conv position
     __shared__ uint32_t dirty_mask[(NPOS + 31) / 32];
     __shared__ unsigned short dirty_list[NPOS];
-    __shared__ int dirty_count;
+    __shared__ int dirty_count, conv_count;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int c3 = 3 * lane;                                // this lane's first channel
+    float* __restrict__ scratch = P.scratch + (size_t)blockIdx.x * NCONV * 96;
 
+    float base3[3];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) base3[j] = P.base[c3 + j];
     // background value of every pooled position: LRN(ReLU(base)) (max-pool of a constant)
     if (warp == 0) {
         float m[3], o[3];
 #pragma unroll
-        for (int j = 0; j < 3; ++j) m[j] = fmaxf(P.base[c3 + j], 0.f);
+        for (int j = 0; j < 3; ++j) m[j] = fmaxf(base3[j], 0.f);
         lrn3(m, o, lane);
 #pragma unroll
         for (int j = 0; j < 3; ++j) {
@@ -102,15 +123,49 @@ front_kernel(const int32_t* __restrict__ rows, long long n, const FrontParams P)
         int32_t pre = 0;
         if (tid < 12 && nxt < n) pre = __ldg(rows + nxt * 12 + tid);
         if (tid < (NPOS + 31) / 32) dirty_mask[tid] = 0;
-        if (tid == 0) dirty_count = 0;
-        build_bitmap<FRONT_THREADS>(rowbuf[cur], bm, lines, red, colmask);          // ends with __syncthreads()
+        if (tid < CONV_W * 2) cdirty[tid] = 0;
+        if (tid == 0) { dirty_count = 0; conv_count = 0; }
+        build_bitmap<FRONT_THREADS>(rowbuf[cur], bm, lines, red, colmask);   // ends with __syncthreads()
 
-        // ---- which pooled positions see a lit pixel? (receptive field: rows/cols 8p .. 8p+18)
+        // ---- conv1 positions whose 11x11 window holds a lit pixel: pixel (r,c) touches
+        //      Y in [ceil((r-10)/4), r/4] x X in [ceil((c-10)/4), c/4]
+        for (int w = tid; w < IMG * BMW; w += FRONT_THREADS) {
+            uint32_t bits = bm[w];
+            const int r = w >> 3, cbase = (w & 7) << 5;
+            const int y_lo = max((r - 7) >> 2, 0), y_hi = min(r >> 2, CONV_W - 1);
+            while (bits) {
+                const int c = cbase + __ffs(bits) - 1;
+                bits &= bits - 1;
+                const int x_lo = max((c - 7) >> 2, 0), x_hi = min(c >> 2, CONV_W - 1);
+                // x_hi - x_lo <= 2: build the (up to 3-bit) column mask once
+                const unsigned long long m = ((2ull << x_hi) - (1ull << x_lo));
+                for (int y = y_lo; y <= y_hi; ++y) {
+                    if ((uint32_t)m) atomicOr(&cdirty[2 * y], (uint32_t)m);
+                    if ((uint32_t)(m >> 32)) atomicOr(&cdirty[2 * y + 1], (uint32_t)(m >> 32));
+                }
+            }
+        }
+        __syncthreads();
+        // ---- compact them: slot <-> position
+        for (int q = tid; q < NCONV; q += FRONT_THREADS) {
+            const int y = q / CONV_W, x = q - y * CONV_W;
+            unsigned short s = CLEAN;
+            if ((cdirty[2 * y + (x >> 5)] >> (x & 31)) & 1u) {
+                s = (unsigned short)atomicAdd(&conv_count, 1);
+                clist[s] = (unsigned short)q;
+            }
+            cslot[q] = s;
+        }
+        // ---- pooled positions that see a dirty conv position (= a lit pixel in their 19x19 field)
         for (int p = tid; p < NPOS; p += FRONT_THREADS) {
             const int py = p / POOLED, px = p - py * POOLED;
             uint32_t any = 0;
 #pragma unroll
-            for (int dr = 0; dr < 19; ++dr) any |= window19(bm, 8 * py + dr, 8 * px);
+            for (int a = 0; a < 3; ++a) {
+                const int y = 2 * py + a, x0 = 2 * px;
+                const unsigned long long rowbits = ((unsigned long long)cdirty[2 * y + 1] << 32) | cdirty[2 * y];
+                any |= (uint32_t)((rowbits >> x0) & 7ull);
+            }
             if (any) {
                 atomicOr(&dirty_mask[p >> 5], 1u << (p & 31));
                 dirty_list[atomicAdd(&dirty_count, 1)] = (unsigned short)p;
@@ -133,50 +188,65 @@ front_kernel(const int32_t* __restrict__ rows, long long n, const FrontParams P)
             *reinterpret_cast<uint4*>(planes[plane] + off) = val;
         }
 
-        // ---- flagged positions: one warp each
+        // ---- phase A: every dirty conv1 position once; a quarter-warp (8 lanes x 12 channels,
+        //      16-byte weight loads) per position, so one instruction stream serves four positions
+        const int nc = conv_count;
+        {
+            const int sub = lane >> 3, c12 = 12 * (lane & 7);
+            for (int i0 = warp * 4; i0 < nc; i0 += (FRONT_THREADS / 32) * 4) {
+                const int i = i0 + sub;
+                if (i >= nc) continue;
+                const int q = clist[i];
+                const int Y = q / CONV_W, X = q - Y * CONV_W;
+                float4 a0 = __ldg(reinterpret_cast<const float4*>(P.base + c12));
+                float4 a1 = __ldg(reinterpret_cast<const float4*>(P.base + c12 + 4));
+                float4 a2 = __ldg(reinterpret_cast<const float4*>(P.base + c12 + 8));
+                for (int kh = 0; kh < 11; ++kh) {
+                    uint32_t w0 = window11(bm, 4 * Y + kh, 4 * X);
+                    if (!w0) continue;
+                    const uint32_t w1 = window11(bm + PLANE, 4 * Y + kh, 4 * X);
+                    const uint32_t w2 = window11(bm + 2 * PLANE, 4 * Y + kh, 4 * X);
+                    while (w0) {
+                        const int kw = __ffs(w0) - 1;
+                        w0 &= w0 - 1;
+                        const float4* wp = reinterpret_cast<const float4*>(P.w255 + ((kh * 11 + kw) * 3) * 96 + c12);
+#pragma unroll
+                        for (int ch = 0; ch < 3; ++ch) {
+                            if (ch == 1 && !((w1 >> kw) & 1u)) continue;
+                            if (ch == 2 && !((w2 >> kw) & 1u)) continue;
+                            const float4 d0 = __ldg(wp + ch * 24), d1 = __ldg(wp + ch * 24 + 1), d2 = __ldg(wp + ch * 24 + 2);
+                            a0.x += d0.x; a0.y += d0.y; a0.z += d0.z; a0.w += d0.w;
+                            a1.x += d1.x; a1.y += d1.y; a1.z += d1.z; a1.w += d1.w;
+                            a2.x += d2.x; a2.y += d2.y; a2.z += d2.z; a2.w += d2.w;
+                        }
+                    }
+                }
+                float4* o = reinterpret_cast<float4*>(scratch + i * 96 + c12);
+                o[0] = a0; o[1] = a1; o[2] = a2;
+            }
+        }
+        __syncthreads();                                    // scratch visible to the whole CTA
+
+        // ---- phase B: flagged pooled positions: max over the 3x3 conv positions, LRN, store
         const int nd = dirty_count;
         for (int i = warp; i < nd; i += FRONT_THREADS / 32) {
             const int p = dirty_list[i];
             const int py = p / POOLED, px = p - py * POOLED;
-            const int r0 = 8 * py, c0 = 8 * px;
-            float acc[9][3];
-#pragma unroll
-            for (int q = 0; q < 9; ++q)
-#pragma unroll
-                for (int j = 0; j < 3; ++j) acc[q][j] = P.base[c3 + j];
-            for (int dr = 0; dr < 19; ++dr) {
-                uint32_t w0 = window19(bm, r0 + dr, c0);
-                if (!w0) continue;
-                const uint32_t w1 = window19(bm + PLANE, r0 + dr, c0);
-                const uint32_t w2 = window19(bm + 2 * PLANE, r0 + dr, c0);
-                while (w0) {
-                    const int dc = __ffs(w0) - 1;
-                    w0 &= w0 - 1;
-                    const bool l1 = (w1 >> dc) & 1u, l2 = (w2 >> dc) & 1u;
-#pragma unroll
-                    for (int a = 0; a < 3; ++a) {
-                        const int kh = dr - 4 * a;
-                        if (kh < 0 || kh > 10) continue;
-#pragma unroll
-                        for (int b = 0; b < 3; ++b) {
-                            const int kw = dc - 4 * b;
-                            if (kw < 0 || kw > 10) continue;
-                            const float* wp = P.w255 + ((kh * 11 + kw) * 3) * 96 + c3;
-                            float d0 = __ldg(wp), d1 = __ldg(wp + 1), d2 = __ldg(wp + 2);
-                            if (l1) { d0 += __ldg(wp + 96); d1 += __ldg(wp + 97); d2 += __ldg(wp + 98); }
-                            if (l2) { d0 += __ldg(wp + 192); d1 += __ldg(wp + 193); d2 += __ldg(wp + 194); }
-                            acc[a * 3 + b][0] += d0;
-                            acc[a * 3 + b][1] += d1;
-                            acc[a * 3 + b][2] += d2;
-                        }
-                    }
-                }
-            }
             float m[3] = {0.f, 0.f, 0.f}, o[3];              // ReLU folded into the max with 0
+            bool all_dirty = true;
 #pragma unroll
-            for (int q = 0; q < 9; ++q)
+            for (int a = 0; a < 3; ++a)
 #pragma unroll
-                for (int j = 0; j < 3; ++j) m[j] = fmaxf(m[j], acc[q][j]);
+                for (int b = 0; b < 3; ++b) {
+                    const unsigned short sl = cslot[(2 * py + a) * CONV_W + 2 * px + b];
+                    if (sl == CLEAN) { all_dirty = false; continue; }
+                    const float* v = scratch + (int)sl * 96 + c3;
+                    m[0] = fmaxf(m[0], __ldcg(v)); m[1] = fmaxf(m[1], __ldcg(v + 1)); m[2] = fmaxf(m[2], __ldcg(v + 2));
+                }
+            if (!all_dirty) {                                // clean conv positions hold the background value
+#pragma unroll
+                for (int j = 0; j < 3; ++j) m[j] = fmaxf(m[j], base3[j]);
+            }
             lrn3(m, o, lane);
             const long long off =
                 (long long)(c3 / 48) * P.group_elems + (img_row0 + py * G2W + px) * P.ld + (c3 % 48);
@@ -211,6 +281,7 @@ int launch_front(const int32_t* rows_dev, long long n, const FrontParams& P, int
     // block scheduler balances the load instead of a static stride over one resident wave
     long long blocks = (long long)num_sms * blocks_per_sm * 8;
     if (blocks > n) blocks = n;
+    if (blocks > P.scratch_blocks) blocks = P.scratch_blocks;
     front_kernel<<<(unsigned)blocks, bitmap::FRONT_THREADS, 0, stream>>>(rows_dev, n, P);
     SVX_LAUNCH_CHECK("front_kernel");
     return 0;

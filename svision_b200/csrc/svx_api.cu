@@ -61,6 +61,8 @@ struct svx_handle {
     bool use_front = true;               // fused sparse front end (front.cu) in the classify path
     float* front_w255 = nullptr;
     float* front_base = nullptr;
+    float* front_scratch = nullptr;      // [front_blocks][3025][96]
+    int front_blocks = 0;
     bool use_pack = true;                // conv2 K-packing: 48-channel positions, 5 row-taps x 240 (K = 1200)
     long long x2_group_elems = 64;       // element offset of channel group 1 in x2
     int x2_ld = 128;                     // elements per x2 position row
@@ -300,6 +302,10 @@ int build_model(svx_handle* h, const svx_weights* w) {
         if ((rc = dev_alloc(h, &h->front_base, base.size(), false))) return rc;
         SVX_CUDA_CHECK(cudaMemcpy(h->front_w255, w255.data(), w255.size() * sizeof(float), cudaMemcpyHostToDevice));
         SVX_CUDA_CHECK(cudaMemcpy(h->front_base, base.data(), base.size() * sizeof(float), cudaMemcpyHostToDevice));
+        // worst case every conv1 position of a site is dirty: 3025 x 96 floats per resident CTA
+        h->front_blocks = h->num_sms * 8;
+        if (h->front_blocks > B) h->front_blocks = (int)B;
+        if ((rc = dev_alloc(h, &h->front_scratch, (size_t)h->front_blocks * 3025 * 96, false))) return rc;
     }
 
     // activations: zero once; pad positions/channels are never written afterwards
@@ -433,7 +439,8 @@ int run_cnn(svx_handle* h, long long n, int32_t* labels, float* probs, float* lo
 // rows -> conv2 operand (fused sparse front end) or rows -> conv1 operand (dense path)
 int encode_front(svx_handle* h, const int32_t* rows_dev, long long m, cudaStream_t st) {
     if (h->use_front) {
-        FrontParams fp{h->front_w255, h->front_base, h->x2_hi, h->x2_lo, h->x2_ld, h->x2_group_elems};
+        FrontParams fp{h->front_w255, h->front_base, h->x2_hi, h->x2_lo, h->front_scratch, h->front_blocks,
+                       h->x2_ld, h->x2_group_elems};
         return launch_front(rows_dev, m, fp, h->num_sms, st);
     }
     return launch_encode(rows_dev, m, h->x1, 2, h->num_sms, st);
