@@ -325,8 +325,8 @@ def run_gpu(args):
                        "sites_per_gpu": n, "micro_batch": MICRO_BATCH, "precision": args.precision,
                        "weights": "synthetic He-init, calibrated fc8 (seed 1234)",
                        "collective": "all_gather of (label, score), 8 B/site" if world > 1 else "none",
-                       "l2": "activation working set per micro-batch ~8 GB and fp16 hi/lo weights "
-                             "228 MB both exceed the 126 MB L2; no flush needed"},
+                       "l2": "activation working set per micro-batch ~4.6 GB and fp16 hi/lo weights "
+                             "226 MB both exceed the 126 MB L2; no flush needed"},
             "e2e": {"value": total_sites / e2e_s, "unit": UNIT,
                     "h2d_bytes_per_step": int(n * world * 48),
                     "d2h_bytes_per_step": int(n * world * 24)},

@@ -123,3 +123,50 @@ def test_softmax_rows_sum_to_one_full_size(clf):
     assert np.abs(probs.sum(1) - 1).max() < 1e-5
     assert ((labels >= 0) & (labels < 5)).all()
     assert np.array_equal(labels, probs.argmax(1).astype(np.int32))
+
+
+@pytest.mark.parametrize("env", [
+    {"SVX_PAIR": "0"},                                   # 1-CTA slab kernel (conv_tc.cu) everywhere
+    {"SVX_PACK": "0"},                                   # conv2 with channels padded 48 -> 64
+    {"SVX_SLAB": "0"},                                   # first-generation per-tap kernel (gemm_tc.cu)
+    {"SVX_FRONT": "0", "SVX_PAIR": "0", "SVX_PACK": "0"},  # fully dense path, 1-CTA kernels
+])
+def test_every_kernel_variant_meets_parity(env, cnn_golden, synthetic_weights, monkeypatch):
+    """Each selectable code path (not only the default) must meet the north-star tolerances."""
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    rows = cnn_golden["rows"][:96]
+    ref_logits = torch.from_numpy(cnn_golden["logits_fp64"][:96])
+    with C.Classifier(synthetic_weights, device=0, max_batch=64) as c:
+        labels, probs, logits = c.classify_device(c.rows_to_device(rows), want_logits=True)
+        assert (logits.cpu().double() - ref_logits).abs().max().item() < LOGIT_TOL, env
+        assert (probs.cpu().double() - torch.softmax(ref_logits, 1)).abs().max().item() < SOFTMAX_TOL, env
+        assert np.array_equal(labels.cpu().numpy(), ref_logits.argmax(1).numpy().astype(np.int32)), env
+
+
+def test_full_size_config2_properties(clf):
+    """BASELINE config 2 size (10 000 sites): determinism, shard-independence and agreement of a
+    strided sample with the CPU oracle (labels equal, softmax within 1e-3)."""
+    rows = sites.make_sites_p1(10_000, seed=sites.SEED_CONFIG2)
+    l1, p1 = clf.classify(rows)
+    l2, p2 = clf.classify(rows)
+    assert np.array_equal(l1, l2) and np.array_equal(p1, p2)                  # deterministic
+    lo, po = clf.classify(rows[5000:])                                         # any contiguous shard
+    assert np.array_equal(lo, l1[5000:]) and np.array_equal(po, p1[5000:])
+    assert np.abs(p1.sum(1) - 1).max() < 1e-5
+    assert len(np.unique(l1)) >= 3                                             # calibrated weights: classes vary
+    idx = np.arange(0, 10_000, 157)
+    from svision_b200 import weights as W
+    ref_l, ref_p, _ = alexnet.classify(encoder_c.encode_f32(rows[idx]), W.synthetic_weights(), torch.float32, batch=64)
+    assert np.array_equal(l1[idx], ref_l.astype(np.int32))
+    assert np.abs(p1[idx] - ref_p).max() < SOFTMAX_TOL
+
+
+def test_one_pass_mode_is_measurably_worse(cnn_golden, synthetic_weights):
+    """The 1-pass mode exists for comparison only: it must NOT be mistaken for parity-clean."""
+    rows = cnn_golden["rows"][:64]
+    ref_logits = torch.from_numpy(cnn_golden["logits_fp64"][:64])
+    with C.Classifier(synthetic_weights, device=0, max_batch=64, precision="1pass") as c:
+        _, probs, _ = c.classify_device(c.rows_to_device(rows), want_logits=True)
+    err = (probs.cpu().double() - torch.softmax(ref_logits, 1)).abs().max().item()
+    assert err > SOFTMAX_TOL
