@@ -371,12 +371,20 @@ conv_tc2_kernel(const __grid_constant__ GemmLayer L) {
 template <int BLOCK_N, int PASSES, bool DBG>
 int launch_impl(const GemmLayer& L, int num_sms, cudaStream_t stream) {
     constexpr int smem_bytes = SMEM_OPERAND_BUDGET + STAGE_BYTES + 1024;
-    static std::once_flag once;
-    static cudaError_t attr_err = cudaSuccess;
-    std::call_once(once, [] {
-        attr_err = cudaFuncSetAttribute(conv_tc2_kernel<BLOCK_N, PASSES, DBG>,
-                                        cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
-    });
+    // function attributes are per device: remember which devices have been configured
+    static std::mutex attr_mutex;
+    static bool attr_done[64] = {};
+    cudaError_t attr_err = cudaSuccess;
+    {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        std::lock_guard<std::mutex> lock(attr_mutex);
+        if (dev < 0 || dev >= 64 || !attr_done[dev]) {
+            attr_err = cudaFuncSetAttribute(conv_tc2_kernel<BLOCK_N, PASSES, DBG>,
+                                            cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+            if (attr_err == cudaSuccess && dev >= 0 && dev < 64) attr_done[dev] = true;
+        }
+    }
     if (attr_err != cudaSuccess)
         return fail(-2, std::string("cudaFuncSetAttribute(conv_tc2_kernel): ") + cudaGetErrorString(attr_err));
     const long long num_mp_tiles = (L.m_rows + 2 * BLOCK_M - 1) / (2 * BLOCK_M);

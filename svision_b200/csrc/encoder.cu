@@ -249,7 +249,10 @@ int launch_encode(const int32_t* rows_dev, long long n, void* out, int mode, int
     // One wave of resident CTAs, each looping over images: the grid is SMs x (CTAs that really fit
     // per SM with the maximum shared-memory carveout), so the grid-stride loop has no ragged
     // second wave (a fixed 8 x SMs grid ran as 1.6 waves: only 5 CTAs were resident).
-    static int blocks_per_sm[3] = {0, 0, 0};
+    static int blocks_cache[64][3] = {};             // per device (function attributes are per device)
+    int dev = 0;
+    cudaGetDevice(&dev);
+    int* blocks_per_sm = blocks_cache[(dev >= 0 && dev < 64) ? dev : 0];
     if (blocks_per_sm[mode] == 0) {
         const void* fn = mode == 0 ? (const void*)encode_kernel<0>
                        : mode == 1 ? (const void*)encode_kernel<1> : (const void*)encode_kernel<2>;

@@ -268,7 +268,10 @@ front_kernel(const int32_t* __restrict__ rows, long long n, const FrontParams P)
 int launch_front(const int32_t* rows_dev, long long n, const FrontParams& P, int num_sms,
                  cudaStream_t stream) {
     if (n <= 0) return 0;
-    static int blocks_per_sm = 0;                 // one wave of resident CTAs (see launch_encode)
+    static int blocks_cache[64] = {};             // per device; one wave of resident CTAs (see launch_encode)
+    int dev = 0;
+    cudaGetDevice(&dev);
+    int& blocks_per_sm = blocks_cache[(dev >= 0 && dev < 64) ? dev : 0];
     if (blocks_per_sm == 0) {
         cudaFuncSetAttribute(front_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
         int nb = 0;
