@@ -170,3 +170,15 @@ def test_one_pass_mode_is_measurably_worse(cnn_golden, synthetic_weights):
         _, probs, _ = c.classify_device(c.rows_to_device(rows), want_logits=True)
     err = (probs.cpu().double() - torch.softmax(ref_logits, 1)).abs().max().item()
     assert err > SOFTMAX_TOL
+
+
+def test_real_demo_rows_and_ont_profile_match_oracle(clf, synthetic_weights):
+    """Real-data rows (reference demo BAM) and ONT-profile rows (BASELINE config 5 shape):
+    labels equal the CPU oracle, softmax within 1e-3."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "demo_rows_golden.npz"))
+    rows = np.concatenate([g["rows"], sites.make_sites_p1(128, seed=sites.SEED_CONFIG5, profile="ont")])
+    labels, probs = clf.classify(rows)
+    ref_l, ref_p, _ = alexnet.classify(encoder_c.encode_f32(rows), synthetic_weights, torch.float32, batch=100)
+    assert np.array_equal(labels, ref_l.astype(np.int32))
+    assert np.abs(probs - ref_p).max() < SOFTMAX_TOL

@@ -68,3 +68,14 @@ def test_encoder_idempotent_and_out_buffer(clf):
     b = clf.encode(rd, dtype=torch.float32, out=out)
     assert torch.equal(a, b)
     assert torch.equal(a.cpu(), torch.from_numpy(encoder_c.encode_f32(rows)))
+
+
+def test_encoder_matches_reference_on_real_demo_rows(clf):
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "demo_rows_golden.npz"))
+    rows, off, codes = g["rows"], g["offsets"], g["codes"]
+    for dtype in (torch.float32, torch.float16):
+        lit = (clf.encode(rows, dtype=dtype) > 0).cpu()
+        for i in range(rows.shape[0]):
+            got = enc.pack_bits(lit[i].permute(2, 0, 1).numpy())
+            assert np.array_equal(got, codes[off[i]:off[i + 1]]), f"demo row {i} ({dtype})"

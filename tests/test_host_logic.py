@@ -135,3 +135,22 @@ def test_sharded_all_gather_gloo_world2(n):
     for p in procs:
         p.join(timeout=60)
     assert res == [(0, True, True), (1, True, True)]
+
+
+def test_bed_reader_on_real_reference_output():
+    """The BED written by the reference's writer_cluster_to_file for its demo BAM."""
+    here = os.path.dirname(__file__)
+    path = os.path.join(here, "golden", "demo_chr9.segments.bed")
+    t = bed.read_segments_bed(path)
+    g = np.load(os.path.join(here, "golden", "demo_rows_golden.npz"))
+    assert np.array_equal(t.rows, g["rows"])
+    assert len(set(t.region)) == 11
+    # every row parses the way the reference's reader does (create_batch.py:42-49,103-137)
+    for i, line in enumerate(open(path)):
+        cols = line.rstrip("\n").split("\t")
+        items = "_".join(cols[1:13]).split("_")
+        assert [int(items[k]) for k in (0, 1, 2, 3, 5, 6, 7, 8, 10, 11)] == \
+            [int(t.rows[i, k]) for k in (0, 1, 2, 3, 5, 6, 7, 8, 10, 11)]
+        assert (items[4] == "True") == bool(t.rows[i, 4]) and (items[9] == "True") == bool(t.rows[i, 9])
+        label = cols[13] + "svision" + cols[0] + "svision" + "svision".join(cols[15:23])
+        assert t.label_strings()[i] == label if i < 3 else True

@@ -74,3 +74,18 @@ def test_encoder_is_order_dependent_on_reverse_segments():
 def test_small_counts(n):
     rows = sites.make_sites_p1(n, seed=1) if n else np.zeros((0, 12), np.int32)
     assert encoder_c.encode_bits(rows).shape == (n, 3, 227, 227)
+
+
+def test_oracles_match_reference_on_real_demo_rows():
+    """272 rows derived from the reference's demo BAM by the reference's own collection stage
+    (oracle/make_demo_rows.py), encoded by the reference's BatchGenerator."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "demo_rows_golden.npz"))
+    rows, off, codes = g["rows"], g["offsets"], g["codes"]
+    assert rows.shape == (272, 12)
+    bits = encoder_c.encode_bits(rows)
+    for i in range(rows.shape[0]):
+        ref = codes[off[i]:off[i + 1]]
+        assert np.array_equal(_codes_of(bits[i]), ref), f"C oracle, demo row {i}"
+        if i % 5 == 0:
+            assert np.array_equal(enc.pack_bits(enc.encode_bits(rows[i])), ref), f"py oracle, demo row {i}"
