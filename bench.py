@@ -39,7 +39,7 @@ sys.path.insert(0, ROOT)
 METRIC = "candidate SV sites/sec (encode+CNN)"
 UNIT = "sites/s"
 SITES_PER_GPU = 10_000
-MICRO_BATCH = 2048
+MICRO_BATCH = int(os.environ.get("SVX_BENCH_MICRO_BATCH", 2048))
 CNN_FLOP_PER_SITE = 1_440_662_592            # SURVEY.md §8(a) layer table (2 x 720 331 296 MACs)
 FC8_FLOP_PER_SITE = 2 * 20_480               # runs on CUDA cores, not in the tensor-core kernel
 ENC_BYTES_PER_SITE = 48 + 227 * 227 * 3 * 2  # 16-bit image is what is emitted
