@@ -23,7 +23,9 @@
  *   - device pointers must belong to the handle's device; the caller owns every buffer it
  *     passes; the library owns weights and workspaces; nothing is allocated on the hot path
  *     after svx_create;
- *   - a handle is not thread-safe and not fork-safe (create it in the process that uses it).
+ *   - a handle is not thread-safe and not fork-safe (create it in the process that uses it);
+ *     calls on one handle are ordered by the library even when they use different streams
+ *     (they share the workspaces), so they never overlap.
  */
 #ifndef SVX_H_
 #define SVX_H_

@@ -71,6 +71,8 @@ struct svx_handle {
     int desc_bo_mode = 0;                // measured on B200: swizzle uses absolute smem address bits, so
                                          // row-shifted slab views need base_offset 0 (mode 1 is wrong)
     cudaStream_t stream = nullptr;       // used by svx_classify (host entry)
+    cudaEvent_t busy = nullptr;          // recorded at the end of every entry that uses the workspaces:
+                                         // the next entry (possibly on another stream) waits on it
     long long last_n = 0;
 
     std::vector<void*> allocs;
@@ -487,11 +489,13 @@ int svx_create(const svx_weights* weights, int device, int64_t max_batch, int pr
     h->precision = precision;
     auto cleanup = [&](int rc) {
         for (void* p : h->allocs) cudaFree(p);
+        if (h->busy) cudaEventDestroy(h->busy);
         if (h->stream) cudaStreamDestroy(h->stream);
         return rc;
     };
     int rc;
     SVX_CUDA_CHECK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    SVX_CUDA_CHECK(cudaEventCreateWithFlags(&h->busy, cudaEventDisableTiming));
     if ((rc = dev_alloc(h.get(), &h->rows_dev, (size_t)max_batch * SVX_ROW_FIELDS))) return cleanup(rc);
     if ((rc = dev_alloc(h.get(), &h->labels_dev, (size_t)max_batch))) return cleanup(rc);
     if ((rc = dev_alloc(h.get(), &h->probs_dev, (size_t)max_batch * SVX_NUM_CLASSES))) return cleanup(rc);
@@ -511,6 +515,7 @@ void svx_destroy(svx_handle* h) {
     cudaDeviceSynchronize();
     for (void* p : h->allocs) cudaFree(p);
     for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
+    if (h->busy) cudaEventDestroy(h->busy);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
 }
@@ -565,6 +570,7 @@ int svx_forward(svx_handle* h, const void* images_dev, int dtype, int64_t n, flo
     DeviceGuard guard(h->device);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const size_t esz = dtype == SVX_IMAGE_F32 ? 4 : 2;
+    SVX_CUDA_CHECK(cudaStreamWaitEvent(st, h->busy, 0));        // workspaces free of earlier entries
     for (int64_t s = 0; s < n; s += h->max_batch) {
         const int64_t m = n - s < h->max_batch ? n - s : h->max_batch;
         const char* src = static_cast<const char*>(images_dev) + (size_t)s * SVX_IMG * SVX_IMG * 3 * esz;
@@ -572,6 +578,7 @@ int svx_forward(svx_handle* h, const void* images_dev, int dtype, int64_t n, flo
         if ((rc = launch_nhwc_to_s2d(src, dtype, m, h->x1, st))) return rc;
         if ((rc = run_cnn(h, m, h->labels_dev, h->probs_dev, logits_dev + s * SVX_NUM_CLASSES, st))) return rc;
     }
+    SVX_CUDA_CHECK(cudaEventRecord(h->busy, st));
     return SVX_OK;
 }
 
@@ -582,6 +589,7 @@ int svx_classify_device(svx_handle* h, const int32_t* rows_dev, int64_t n, int32
         return fail(SVX_ERR_INVALID, "svx_classify_device: bad arguments");
     DeviceGuard guard(h->device);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    SVX_CUDA_CHECK(cudaStreamWaitEvent(st, h->busy, 0));
     for (int64_t s = 0; s < n; s += h->max_batch) {
         const int64_t m = n - s < h->max_batch ? n - s : h->max_batch;
         int rc;
@@ -591,6 +599,7 @@ int svx_classify_device(svx_handle* h, const int32_t* rows_dev, int64_t n, int32
                           logits_dev ? logits_dev + s * SVX_NUM_CLASSES : nullptr, st, h->use_front)))
             return rc;
     }
+    SVX_CUDA_CHECK(cudaEventRecord(h->busy, st));
     return SVX_OK;
 }
 
@@ -601,6 +610,7 @@ int svx_classify(svx_handle* h, const int32_t* rows_host, int64_t n, int32_t* la
         return fail(SVX_ERR_INVALID, "svx_classify: bad arguments");
     DeviceGuard guard(h->device);
     cudaStream_t st = h->stream;
+    SVX_CUDA_CHECK(cudaStreamWaitEvent(st, h->busy, 0));
     for (int64_t s = 0; s < n; s += h->max_batch) {
         const int64_t m = n - s < h->max_batch ? n - s : h->max_batch;
         int rc;
@@ -614,6 +624,7 @@ int svx_classify(svx_handle* h, const int32_t* rows_host, int64_t n, int32_t* la
         SVX_CUDA_CHECK(cudaMemcpyAsync(probs_host + s * SVX_NUM_CLASSES, h->probs_dev,
                                        (size_t)m * SVX_NUM_CLASSES * sizeof(float), cudaMemcpyDeviceToHost, st));
     }
+    SVX_CUDA_CHECK(cudaEventRecord(h->busy, st));
     SVX_CUDA_CHECK(cudaStreamSynchronize(st));
     return SVX_OK;
 }
