@@ -13,7 +13,6 @@ constexpr int NEL = NPIX * 3;            // 154587 elements per image
 constexpr int BMW = 8;                   // 32-bit words per bitmap row (256 >= 227 columns)
 constexpr int BMROWS = 228;              // +1 all-zero row (space-to-depth pad row / straddle reads)
 constexpr int PLANE = BMROWS * BMW;      // words per channel plane
-constexpr int ENC_THREADS = 128;         // encoder: small CTAs, ~8 resident per SM hide the serial line set-up
 constexpr int FRONT_THREADS = 256;       // fused front end: more warps per site for the lit-pixel work
 
 struct LineParams {

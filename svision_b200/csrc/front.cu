@@ -70,12 +70,43 @@ __device__ __forceinline__ void lrn3(const float (&m)[3], float (&out)[3], int l
 
 constexpr int CONV_W = 55, NCONV = CONV_W * CONV_W;      // conv1 output grid, 3025 positions
 constexpr unsigned short CLEAN = 0xFFFF;
+// Scratch slots per CTA.  A segment is a digital line of <= 227 pixels, i.e. <= 57 steps on the conv1
+// grid, and every pixel marks at most a 3x3 block of positions, so one line dirties < 300 positions and
+// a site < 600.  Keeping the per-CTA regions small keeps the ~600 concurrent regions inside the TLB
+// reach; positions beyond the capacity (not reachable with two segments) are recomputed in phase B.
+constexpr int SCRATCH_SLOTS = 640;
 
 // bits [c, c+11) of bitmap row r (c + 10 <= 226)
 __device__ __forceinline__ uint32_t window11(const uint32_t* plane, int r, int c) {
     const uint32_t* rowp = plane + r * BMW;
     const int wi = c >> 5;
     return __funnelshift_r(rowp[wi], rowp[wi + 1], c & 31) & 0x7FFu;
+}
+
+// conv1 value (before ReLU) of position (Y, X) for NCH consecutive channels starting at c0
+template <int NCH>
+__device__ __forceinline__ void conv1_at(const uint32_t* bm, const FrontParams& P, int Y, int X, int c0,
+                                         float (&acc)[NCH]) {
+#pragma unroll
+    for (int j = 0; j < NCH; ++j) acc[j] = __ldg(P.base + c0 + j);
+    for (int kh = 0; kh < 11; ++kh) {
+        uint32_t w0 = window11(bm, 4 * Y + kh, 4 * X);
+        if (!w0) continue;
+        const uint32_t w1 = window11(bm + PLANE, 4 * Y + kh, 4 * X);
+        const uint32_t w2 = window11(bm + 2 * PLANE, 4 * Y + kh, 4 * X);
+        while (w0) {
+            const int kw = __ffs(w0) - 1;
+            w0 &= w0 - 1;
+            const float* wp = P.w255 + ((kh * 11 + kw) * 3) * 96 + c0;
+#pragma unroll
+            for (int ch = 0; ch < 3; ++ch) {
+                if (ch == 1 && !((w1 >> kw) & 1u)) continue;
+                if (ch == 2 && !((w2 >> kw) & 1u)) continue;
+#pragma unroll
+                for (int j = 0; j < NCH; ++j) acc[j] += __ldg(wp + ch * 96 + j);
+            }
+        }
+    }
 }
 
 __global__ void __launch_bounds__(FRONT_THREADS, 4)
@@ -94,7 +125,7 @@ front_kernel(const int32_t* __restrict__ rows, long long n, const FrontParams P)
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int c3 = 3 * lane;                                // this lane's first channel
-    float* __restrict__ scratch = P.scratch + (size_t)blockIdx.x * NCONV * 96;
+    float* __restrict__ scratch = P.scratch + (size_t)blockIdx.x * SCRATCH_SLOTS * 96;
 
     float base3[3];
 #pragma unroll
@@ -190,7 +221,7 @@ front_kernel(const int32_t* __restrict__ rows, long long n, const FrontParams P)
 
         // ---- phase A: every dirty conv1 position once; a quarter-warp (8 lanes x 12 channels,
         //      16-byte weight loads) per position, so one instruction stream serves four positions
-        const int nc = conv_count;
+        const int nc = min(conv_count, SCRATCH_SLOTS);
         {
             const int sub = lane >> 3, c12 = 12 * (lane & 7);
             for (int i0 = warp * 4; i0 < nc; i0 += (FRONT_THREADS / 32) * 4) {
@@ -240,8 +271,14 @@ front_kernel(const int32_t* __restrict__ rows, long long n, const FrontParams P)
                 for (int b = 0; b < 3; ++b) {
                     const unsigned short sl = cslot[(2 * py + a) * CONV_W + 2 * px + b];
                     if (sl == CLEAN) { all_dirty = false; continue; }
-                    const float* v = scratch + (int)sl * 96 + c3;
-                    m[0] = fmaxf(m[0], __ldcg(v)); m[1] = fmaxf(m[1], __ldcg(v + 1)); m[2] = fmaxf(m[2], __ldcg(v + 2));
+                    if (sl < SCRATCH_SLOTS) {
+                        const float* v = scratch + (int)sl * 96 + c3;
+                        m[0] = fmaxf(m[0], __ldcg(v)); m[1] = fmaxf(m[1], __ldcg(v + 1)); m[2] = fmaxf(m[2], __ldcg(v + 2));
+                    } else {                             // beyond the scratch capacity: recompute here
+                        float v[3];
+                        conv1_at<3>(bm, P, 2 * py + a, 2 * px + b, c3, v);
+                        m[0] = fmaxf(m[0], v[0]); m[1] = fmaxf(m[1], v[1]); m[2] = fmaxf(m[2], v[2]);
+                    }
                 }
             if (!all_dirty) {                                // clean conv positions hold the background value
 #pragma unroll

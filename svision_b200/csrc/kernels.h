@@ -19,7 +19,7 @@ struct FrontParams {
     const float* base;         // [96] = bias + sum_k lo_ch * W[k]  (conv1 of the all-background image)
     __half* x2_hi;             // conv2 operand, see DESIGN.md §3
     __half* x2_lo;
-    float* scratch;            // [scratch_blocks][3025][96] conv1 values of dirty positions (L2-resident)
+    float* scratch;            // [scratch_blocks][640][96] conv1 values of dirty positions (L2-resident)
     int scratch_blocks;        // upper bound for the grid
     int ld;                    // elements per position row (128 padded layout, 48 packed layout)
     long long group_elems;     // element offset of channel group 1 (64 padded, plane size packed)

@@ -304,10 +304,10 @@ int build_model(svx_handle* h, const svx_weights* w) {
         if ((rc = dev_alloc(h, &h->front_base, base.size(), false))) return rc;
         SVX_CUDA_CHECK(cudaMemcpy(h->front_w255, w255.data(), w255.size() * sizeof(float), cudaMemcpyHostToDevice));
         SVX_CUDA_CHECK(cudaMemcpy(h->front_base, base.data(), base.size() * sizeof(float), cudaMemcpyHostToDevice));
-        // worst case every conv1 position of a site is dirty: 3025 x 96 floats per resident CTA
-        h->front_blocks = h->num_sms * 8;
+        // 640 scratch slots x 96 floats per CTA of the front kernel (see front.cu SCRATCH_SLOTS)
+        h->front_blocks = h->num_sms * 32;
         if (h->front_blocks > B) h->front_blocks = (int)B;
-        if ((rc = dev_alloc(h, &h->front_scratch, (size_t)h->front_blocks * 3025 * 96, false))) return rc;
+        if ((rc = dev_alloc(h, &h->front_scratch, (size_t)h->front_blocks * 640 * 96, false))) return rc;
     }
 
     // activations: zero once; pad positions/channels are never written afterwards
