@@ -73,7 +73,7 @@ __global__ void __launch_bounds__(256) pool_kernel(const PoolParams p, long long
 #pragma unroll
             for (int j = 0; j < CPL; ++j) {
                 const float s5 = sq[j] + sq[j + 1] + sq[j + 2] + sq[j + 3] + sq[j + 4];
-                out[j] = m[j] * powf(1.0f + 2e-5f * s5, -0.75f);
+                out[j] = m[j] * pow_m075(1.0f + 2e-5f * s5);
             }
         } else {
 #pragma unroll

@@ -64,7 +64,7 @@ __device__ __forceinline__ void lrn3(const float (&m)[3], float (&out)[3], int l
 #pragma unroll
     for (int j = 0; j < 3; ++j) {
         const float s5 = sq[j] + sq[j + 1] + sq[j + 2] + sq[j + 3] + sq[j + 4];
-        out[j] = m[j] * powf(1.0f + 2e-5f * s5, -0.75f);
+        out[j] = m[j] * pow_m075(1.0f + 2e-5f * s5);
     }
 }
 
