@@ -20,9 +20,11 @@
 //   * warps 2-9 of BOTH CTAs: epilogue over the CTA's own TMEM (128 rows): warp = (lane quarter,
 //     column half), so running sums are BLOCK_N/2 <= 128 registers per thread; both CTAs arrive
 //     on the leader's TMEM-empty barrier (mapa + mbarrier.arrive.shared::cluster).  Output goes
-//     through a per-warp shared-memory staging tile so that every global store instruction writes
-//     whole 128-byte lines (thread-per-row stores touched 32 lines per instruction and made the
-//     per-tile store phase, ~7k cycles, the bottleneck of the first pair version).
+//     through a small per-warp shared-memory staging tile (16 columns per pass) so that every
+//     global store instruction writes whole 32-byte sectors of few lines (thread-per-row stores
+//     touched 32 lines per instruction and made the per-tile store phase, ~7k cycles, the
+//     bottleneck of the first pair version); the tile is kept small (20 KB per CTA) so the weight
+//     ring keeps 4+ stages.
 #include "common.cuh"
 #include "kernels.h"
 
@@ -39,10 +41,13 @@ constexpr int PAIR_THREADS = 320;                  // warp 0 TMA, warp 1 MMA/all
 constexpr int EPI_THREADS = 256;
 constexpr int MAX_SLAB_SLOTS = 4;
 constexpr int MAX_B_STAGES = 8;
-constexpr int STAGE_ROW_BYTES = 144;                // 128 B payload + 16 B pad (bank-conflict-free v4 writes)
-constexpr int STAGE_WARP_BYTES = 32 * STAGE_ROW_BYTES;
-constexpr int STAGE_BYTES = 8 * STAGE_WARP_BYTES;   // one 32-row staging tile per epilogue warp
-constexpr int SMEM_OPERAND_BUDGET = 222 * 1024 - STAGE_BYTES;
+// epilogue staging: one 32-row tile per epilogue warp, STG columns per pass.  STG = 32: rows of
+// 128 B payload + 16 B pad (whole 128-byte lines per store); STG = 16: 64 B + 16 B (half the
+// shared memory, chosen where it buys the weight ring a 4th stage)
+constexpr int SMEM_TOTAL = 222 * 1024;
+__host__ __device__ constexpr int stage_row_bytes(int stg) { return stg == 32 ? 144 : 80; }
+__host__ __device__ constexpr int stage_bytes(int stg) { return 8 * 32 * stage_row_bytes(stg); }
+__host__ __device__ constexpr int operand_budget(int stg) { return SMEM_TOTAL - stage_bytes(stg); }
 constexpr int TMEM_COLS = 512;
 constexpr uint32_t DESC_HI = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);   // SBO, version, SW128
 
@@ -53,9 +58,12 @@ __device__ __forceinline__ uint32_t desc_lo(uint32_t smem_addr) {
     return ((smem_addr >> 4) & 0x3FFFu) | (1u << 16);
 }
 
-template <int BLOCK_N, int PASSES, bool DBG>
+template <int BLOCK_N, int PASSES, int STG, bool DBG>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PAIR_THREADS, 1)
 conv_tc2_kernel(const __grid_constant__ GemmLayer L) {
+    constexpr int STAGE_ROW_BYTES = stage_row_bytes(STG);
+    constexpr int STAGE_WARP_BYTES = 32 * STAGE_ROW_BYTES;
+    constexpr int SMEM_OPERAND_BUDGET = operand_budget(STG);
     constexpr int HALF_N = BLOCK_N / 2;                        // weight rows held by each CTA
     constexpr int B_PLANE_BYTES = HALF_N * BLOCK_K * 2;
     constexpr bool A_LO = PASSES == 3;
@@ -291,6 +299,7 @@ conv_tc2_kernel(const __grid_constant__ GemmLayer L) {
                 }
                 row_mask = __ballot_sync(0xffffffffu, ok);
             }
+            if constexpr (STG == 32) {
 #pragma unroll
             for (int c = 0; c < COLS_PER_THREAD / 32; ++c) {
                 float v[32];
@@ -350,6 +359,66 @@ conv_tc2_kernel(const __grid_constant__ GemmLayer L) {
                     __syncwarp();
                 }
             }
+            } else {
+#pragma unroll
+            for (int c = 0; c < COLS_PER_THREAD / 16; ++c) {
+                float v[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    float x = sum[c * 16 + j] + bias_s[col0 + c * 16 + j];
+                    v[j] = L.relu ? fmaxf(x, 0.f) : x;
+                }
+                const long long gcol = n0 + col0 + c * 16;
+                uint4* my = reinterpret_cast<uint4*>(stg + lane * STAGE_ROW_BYTES);
+                if (L.out_f32) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        my[j] = make_uint4(__float_as_uint(v[4 * j]), __float_as_uint(v[4 * j + 1]),
+                                           __float_as_uint(v[4 * j + 2]), __float_as_uint(v[4 * j + 3]));
+                    __syncwarp();
+                    // 4 lanes cover one row's 64 B; one instruction writes 8 rows x 2 whole sectors
+#pragma unroll
+                    for (int it = 0; it < 4; ++it) {
+                        const int r = it * 8 + (lane >> 2), ch = lane & 3;
+                        if ((row_mask >> r) & 1u) {
+                            const uint4 val = *reinterpret_cast<const uint4*>(stg + r * STAGE_ROW_BYTES + ch * 16);
+                            *reinterpret_cast<uint4*>(L.out_f32 + (row0 + r) * (long long)L.ldc + gcol + ch * 4) = val;
+                        }
+                    }
+                    __syncwarp();
+                }
+                if (L.out_hi) {
+                    uint32_t ph[8], pl[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const __half h0 = __float2half_rn(v[2 * j]);
+                        const __half h1 = __float2half_rn(v[2 * j + 1]);
+                        const __half l0 = __float2half_rn(v[2 * j] - __half2float(h0));
+                        const __half l1 = __float2half_rn(v[2 * j + 1] - __half2float(h1));
+                        ph[j] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
+                        pl[j] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
+                    }
+                    my[0] = make_uint4(ph[0], ph[1], ph[2], ph[3]);       // hi: bytes 0..31
+                    my[1] = make_uint4(ph[4], ph[5], ph[6], ph[7]);
+                    my[2] = make_uint4(pl[0], pl[1], pl[2], pl[3]);       // lo: bytes 32..63
+                    my[3] = make_uint4(pl[4], pl[5], pl[6], pl[7]);
+                    __syncwarp();
+                    // 2 lanes cover one row's 32 B of a plane; one instruction writes 16 rows x 1 sector
+#pragma unroll
+                    for (int it = 0; it < 2; ++it) {
+                        const int r = it * 16 + (lane >> 1), ch = lane & 1;
+                        if ((row_mask >> r) & 1u) {
+                            const long long o = (row0 + r) * (long long)L.ldc + gcol + ch * 8;
+                            *reinterpret_cast<uint4*>(L.out_hi + o) =
+                                *reinterpret_cast<const uint4*>(stg + r * STAGE_ROW_BYTES + ch * 16);
+                            *reinterpret_cast<uint4*>(L.out_lo + o) =
+                                *reinterpret_cast<const uint4*>(stg + r * STAGE_ROW_BYTES + 32 + ch * 16);
+                        }
+                    }
+                    __syncwarp();
+                }
+            }
+            }
             if (DBG) c_epi_store += clock64() - t0;
         }
         if (DBG && L.dbg && leader && warp == 2 && lane == 0) {
@@ -368,9 +437,9 @@ conv_tc2_kernel(const __grid_constant__ GemmLayer L) {
     }
 }
 
-template <int BLOCK_N, int PASSES, bool DBG>
+template <int BLOCK_N, int PASSES, int STG, bool DBG>
 int launch_impl(const GemmLayer& L, int num_sms, cudaStream_t stream) {
-    constexpr int smem_bytes = SMEM_OPERAND_BUDGET + STAGE_BYTES + 1024;
+    constexpr int smem_bytes = SMEM_TOTAL + 1024;
     // function attributes are per device: remember which devices have been configured
     static std::mutex attr_mutex;
     static bool attr_done[64] = {};
@@ -380,7 +449,7 @@ int launch_impl(const GemmLayer& L, int num_sms, cudaStream_t stream) {
         cudaGetDevice(&dev);
         std::lock_guard<std::mutex> lock(attr_mutex);
         if (dev < 0 || dev >= 64 || !attr_done[dev]) {
-            attr_err = cudaFuncSetAttribute(conv_tc2_kernel<BLOCK_N, PASSES, DBG>,
+            attr_err = cudaFuncSetAttribute(conv_tc2_kernel<BLOCK_N, PASSES, STG, DBG>,
                                             cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
             if (attr_err == cudaSuccess && dev >= 0 && dev < 64) attr_done[dev] = true;
         }
@@ -393,26 +462,32 @@ int launch_impl(const GemmLayer& L, int num_sms, cudaStream_t stream) {
     if (total > 0x7fffffffLL) return fail(-1, "conv2: too many tiles");
     long long pairs = num_sms / 2;
     if (pairs > total) pairs = total;
-    conv_tc2_kernel<BLOCK_N, PASSES, DBG><<<(unsigned)(2 * pairs), PAIR_THREADS, smem_bytes, stream>>>(L);
+    conv_tc2_kernel<BLOCK_N, PASSES, STG, DBG><<<(unsigned)(2 * pairs), PAIR_THREADS, smem_bytes, stream>>>(L);
     SVX_LAUNCH_CHECK("conv_tc2_kernel");
     return 0;
 }
 
-template <int BLOCK_N>
-int launch_passes(const GemmLayer& L, int num_sms, cudaStream_t stream) {
+template <int BLOCK_N, int STG>
+int launch_passes_stg(const GemmLayer& L, int num_sms, cudaStream_t stream) {
     const int passes = L.use_a_lo ? 3 : (L.use_b_lo ? 2 : 1);
     if (L.dbg) {
         switch (passes) {
-            case 3: return launch_impl<BLOCK_N, 3, true>(L, num_sms, stream);
-            case 2: return launch_impl<BLOCK_N, 2, true>(L, num_sms, stream);
-            default: return launch_impl<BLOCK_N, 1, true>(L, num_sms, stream);
+            case 3: return launch_impl<BLOCK_N, 3, STG, true>(L, num_sms, stream);
+            case 2: return launch_impl<BLOCK_N, 2, STG, true>(L, num_sms, stream);
+            default: return launch_impl<BLOCK_N, 1, STG, true>(L, num_sms, stream);
         }
     }
     switch (passes) {
-        case 3: return launch_impl<BLOCK_N, 3, false>(L, num_sms, stream);
-        case 2: return launch_impl<BLOCK_N, 2, false>(L, num_sms, stream);
-        default: return launch_impl<BLOCK_N, 1, false>(L, num_sms, stream);
+        case 3: return launch_impl<BLOCK_N, 3, STG, false>(L, num_sms, stream);
+        case 2: return launch_impl<BLOCK_N, 2, STG, false>(L, num_sms, stream);
+        default: return launch_impl<BLOCK_N, 1, STG, false>(L, num_sms, stream);
     }
+}
+
+template <int BLOCK_N>
+int launch_passes(const GemmLayer& L, int num_sms, cudaStream_t stream) {
+    return L.stage_cols == 16 ? launch_passes_stg<BLOCK_N, 16>(L, num_sms, stream)
+                              : launch_passes_stg<BLOCK_N, 32>(L, num_sms, stream);
 }
 
 }  // namespace
@@ -431,7 +506,13 @@ int plan_slab_pair(GemmLayer& L) {
     const int slot = L.slab_rows * 128 * (L.use_a_lo ? 2 : 1);
     const int stage = (L.block_n / 2) * BLOCK_K * 2 * (L.use_b_lo ? 2 : 1);
     L.n_slab_slots = L.taps == 1 ? 3 : 2;
-    int nb = (SMEM_OPERAND_BUDGET - L.n_slab_slots * slot) / stage;
+    // wide (32-column) epilogue staging unless the narrow one buys the weight ring a 4th stage
+    L.stage_cols = 32;
+    int nb = (operand_budget(32) - L.n_slab_slots * slot) / stage;
+    if (nb < 4) {
+        const int nb16 = (operand_budget(16) - L.n_slab_slots * slot) / stage;
+        if (nb16 > nb) { nb = nb16; L.stage_cols = 16; }
+    }
     if (nb > MAX_B_STAGES) nb = MAX_B_STAGES;
     if (nb < 2) return fail(-1, "conv2: shared memory budget too small for this layer");
     L.n_b_stages = nb;

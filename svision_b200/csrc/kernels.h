@@ -69,6 +69,7 @@ struct GemmLayer {
     int slab_rows;             // multiple of 8, >= 128 + max(row_off) - min(row_off), <= 256
     int off_min;               // min(row_off)
     int n_slab_slots, n_b_stages;
+    int stage_cols;            // pair kernel: epilogue staging width (32, or 16 to free smem for weight stages)
     int desc_base_offset_mode; // 1: descriptor base_offset = (addr >> 7) & 7 for shifted starts
     // optional cycle counters (development): 8 x unsigned long long, atomically accumulated per CTA
     //  0 MMA-role total  1 MMA wait operands  2 MMA wait TMEM-empty  3 k-blocks
