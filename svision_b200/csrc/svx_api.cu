@@ -30,7 +30,11 @@ constexpr int P1 = S2D * S2D;                 // 3249 positions per site in x1 /
 constexpr int G2 = 29, P2 = G2 * G2;          // conv2 grid: 27 + 2 shared pad rows/cols -> 841
 constexpr int G3 = 14, P3 = G3 * G3;          // conv3-5 grid: 13 + 1 -> 196
 
-constexpr int kChunkKBlocks = 4;              // K = 256 per TMEM accumulation chain
+constexpr int kChunkKBlocks = 4;              // K = 256 per TMEM accumulation chain (default)
+static int chunk_kblocks() {                  // SVX_CHUNK overrides (development: precision/speed trade)
+    if (const char* e = std::getenv("SVX_CHUNK")) { const int v = std::atoi(e); if (v >= 1 && v <= 64) return v; }
+    return kChunkKBlocks;
+}
 
 enum { L_CONV1 = 0, L_CONV2, L_CONV3, L_CONV4, L_CONV5, L_FC6, L_FC7, L_COUNT };
 
@@ -207,7 +211,7 @@ int setup_layer(svx_handle* h, int li, const __half* a_hi, const __half* a_lo, l
     const long long K = packed ? (long long)kPackTaps * kPackK : (long long)s.taps * s.cg_pad;
     int rc;
     L.block_n = s.block_n;
-    L.chunk_kblocks = kChunkKBlocks;
+    L.chunk_kblocks = chunk_kblocks();
     L.groups = s.groups;
     L.n_per_group = s.n_total / s.groups;
     L.taps = s.taps;
@@ -706,7 +710,7 @@ int svx_gemm_selftest(int device, const float* a_dev, const float* b_dev, float*
     if ((rc = make_tensor_map_2d(&L.tm_a_lo, a_lo, m, k, k, GEMM_BLOCK_M))) return free_all(rc);
     if ((rc = make_tensor_map_2d(&L.tm_b_hi, b_hi, n, k, k, block_n))) return free_all(rc);
     if ((rc = make_tensor_map_2d(&L.tm_b_lo, b_lo, n, k, k, block_n))) return free_all(rc);
-    L.block_n = block_n; L.chunk_kblocks = kChunkKBlocks; L.groups = 1; L.n_per_group = (int)n; L.taps = 1; L.cblocks = (int)(k / GEMM_BLOCK_K);
+    L.block_n = block_n; L.chunk_kblocks = chunk_kblocks(); L.groups = 1; L.n_per_group = (int)n; L.taps = 1; L.cblocks = (int)(k / GEMM_BLOCK_K);
     L.a_group_cols = 0; L.row_off[0] = 0;
     L.use_a_lo = L.use_b_lo = precision == SVX_PRECISION_3PASS ? 1 : 0;
     L.m_rows = m; L.bias = bias; L.relu = 0; L.out_f32 = c_dev; L.ldc = (int)n;
@@ -746,7 +750,7 @@ int svx_conv_selftest(int device, const float* a_dev, const float* b_dev, float*
     if ((rc = launch_split_hilo(b_dev, n * k, b_hi, b_lo, st))) return free_all(rc);
     GemmLayer L;
     std::memset(&L, 0, sizeof(L));
-    L.block_n = block_n; L.chunk_kblocks = kChunkKBlocks; L.groups = 1; L.n_per_group = (int)n;
+    L.block_n = block_n; L.chunk_kblocks = chunk_kblocks(); L.groups = 1; L.n_per_group = (int)n;
     L.taps = taps; L.cblocks = (int)(k_per_tap / GEMM_BLOCK_K); L.a_group_cols = 0;
     for (int t = 0; t < taps; ++t) L.row_off[t] = row_off[t];
     L.use_a_lo = L.use_b_lo = precision == SVX_PRECISION_3PASS ? 1 : 0;
