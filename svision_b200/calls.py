@@ -1,0 +1,353 @@
+"""Region aggregation, type refinement, VCF record assembly and a one-pass genotyper: the host step
+immediately *after* the encode+classify path.
+
+What the reference does per region, and what this module restates:
+
+    aggregate_region   <- Predict.get_region_potential_svtypes   (src/network/predict.py:29-145)
+    refine_types       <- refine_type                            (src/network/output.py:352-467)
+    region_records     <- write_results_to_vcf                   (src/network/output.py:469-598)
+    AlignmentTable     <- genotyper                              (src/network/genotype.py:17-73)
+    call_chromosome    <- the per-row loop of Predict.run         (src/network/predict.py:213-300)
+
+Differences in *how*, none in *what*: the per-row loop runs over plain Python lists taken from the
+BED columns in one ``tolist()`` each (no per-row string splitting, no numpy scalar boxing); and the
+genotyper reads the BAM once per chromosome into sorted arrays and answers every candidate with two
+binary searches, instead of re-opening the BAM for every VCF record (``genotype.py:22``).
+
+Numeric types are kept exactly as the reference has them, because they are visible in the text it
+prints: class scores stay ``numpy.float32`` through ``round(…, 2)``, ``numpy.mean`` and
+``(1 - round(mean, 2)) * 100`` (``predict.py:251``, ``output.py:473-474``), the signature-score
+spread is a float64 ``numpy.std`` (``output.py:551``), and QUAL is printed with ``str()``.
+"""
+from __future__ import annotations
+
+from collections import Counter
+from typing import Callable, Iterable, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+TYPE_NAMES = ("DEL", "INS", "INV", "DUP", "tDUP")            # predict.py:133-142
+MAX_GENOTYPE_ALIGNMENTS = 500                                 # genotype.py:34
+
+
+# ------------------------------------------------------------------------------------------------
+# aggregation
+# ------------------------------------------------------------------------------------------------
+def aggregate_region(reads: dict) -> list:
+    """``reads``: ``{read_id: {class_id: [bkp_start, bkp_end, bkp_len]}}`` in insertion order.
+
+    Reads that carry the same *set* of classes form one candidate; its breakpoints are a running
+    integer mean taken read by read, ``int((new + old*n) / (n+1))`` with true division
+    (predict.py:104-106) -- not the mean of all reads, so the order of reads matters.  Candidates
+    come back ordered by support, ties in first-seen order (predict.py:114), as
+    ``[("INS+tDUP", [read ids], [[start, end, len], ...]), ...]``."""
+    groups: dict = {}
+    for read_id, calls in reads.items():
+        if len(calls) == 1:                                # the common case: one class per read
+            (k, b), = calls.items()
+            kinds, current = (k,), [b]
+        else:
+            kinds = tuple(sorted(calls))
+            current = [calls[k] for k in kinds]
+        g = groups.get(kinds)
+        if g is None:
+            groups[kinds] = [[read_id], current]
+            continue
+        n = len(g[0])
+        g[1] = [[int((c[j] + o[j] * n) / (n + 1)) for j in range(3)] for c, o in zip(current, g[1])]
+        g[0].append(read_id)
+    ranked = sorted(groups.items(), key=lambda kv: -len(kv[1][0]))          # stable
+    return [("+".join(TYPE_NAMES[k] for k in kinds), ids, bkps) for kinds, (ids, bkps) in ranked]
+
+
+def refine_types(kinds: Sequence[str], bkps: Sequence[list], min_sv_size: int) -> Tuple[list, list]:
+    """An INS next to a DUP/tDUP is usually the duplicated copy itself (output.py:352-467):
+
+    * a DUP whose end lies within 10 bp of the INS position becomes a tDUP (only when the candidate
+      has a plain DUP at all: output.py:388-405,429-441);
+    * if the inserted length exceeds the duplicated length by more than ``min_sv_size`` the INS
+      stays, shortened to the novel part; otherwise the INS is dropped.
+
+    Class ids are sorted (DEL<INS<INV<DUP<tDUP) and unique within a candidate, so the INS always
+    precedes the duplications it is compared with."""
+    kinds, bkps = list(kinds), list(bkps)
+    if "INS" not in kinds or not ("DUP" in kinds or "tDUP" in kinds):
+        return kinds, bkps
+    ins_len = dup_len = 0
+    ins_pos = -1
+    for i, k in enumerate(kinds):
+        if k == "INS":
+            ins_pos = int(bkps[i][0])
+            ins_len += int(bkps[i][2])
+        elif k == "DUP" or k == "tDUP":
+            dup_len += int(bkps[i][2])
+            if k == "DUP" and ins_pos != -1 and abs(ins_pos - int(bkps[i][1])) < 10:
+                kinds[i] = "tDUP"
+    if ins_len - dup_len > min_sv_size:
+        out_b = [list(b) for b in bkps]
+        out_b[kinds.index("INS")][2] = ins_len - dup_len
+        return kinds, out_b
+    keep = [i for i, k in enumerate(kinds) if k != "INS"]
+    return [kinds[i] for i in keep], [bkps[i] for i in keep]
+
+
+# ------------------------------------------------------------------------------------------------
+# genotyping: one pass over the BAM per chromosome
+# ------------------------------------------------------------------------------------------------
+class AlignmentTable:
+    """All alignments of one contig as arrays in BAM (coordinate) order.
+
+    ``genotype`` answers what ``genotyper`` (genotype.py:17-73) answers, without touching the BAM
+    again: the alignments overlapping ``[start-1000, end+1000)`` are found with two binary searches
+    (``reference_start`` is sorted; a running maximum of ``reference_end`` bounds the left side),
+    the first 500 usable ones that do not belong to a supporting read are taken, and the
+    reference-supporting reads are counted by distinct query name."""
+
+    def __init__(self, contig_length: int, reference_start, reference_end, mapping_quality,
+                 is_unmapped, is_secondary, query_names: Sequence[str]):
+        self.contig_length = int(contig_length)
+        self.start = np.ascontiguousarray(reference_start, dtype=np.int64)
+        self.end = np.ascontiguousarray(reference_end, dtype=np.int64)
+        if self.start.size and np.any(np.diff(self.start) < 0):
+            raise ValueError("alignments must be in coordinate order (the reference requires a sorted BAM: SVision:141-146)")
+        self.mapq = np.ascontiguousarray(mapping_quality, dtype=np.int64)
+        self.skip = np.asarray(is_unmapped, dtype=bool) | np.asarray(is_secondary, dtype=bool)
+        names, self.name_id = np.unique(np.asarray(query_names, dtype=object).astype(str), return_inverse=True)
+        self._name_to_id = {n: i for i, n in enumerate(names.tolist())}
+        self._end_running_max = np.maximum.accumulate(self.end) if self.end.size else self.end
+
+    @classmethod
+    def from_bam(cls, bam_path: str, contig: str) -> "AlignmentTable":
+        """One ``fetch`` over the whole contig.  Needs ``pysam`` (a dependency of the reference:
+        ``setup.py:36``); raises ImportError where it is absent."""
+        import pysam
+        bam = pysam.AlignmentFile(bam_path, "r")
+        s, e, q, u, sec, names = [], [], [], [], [], []
+        for a in bam.fetch(contig=contig):
+            s.append(a.reference_start)
+            e.append(a.reference_end if a.reference_end is not None else a.reference_start)
+            q.append(a.mapping_quality)
+            u.append(a.is_unmapped)
+            sec.append(a.is_secondary)
+            names.append(a.query_name)
+        return cls(bam.get_reference_length(contig), s, e, q, u, sec, names)
+
+    def __len__(self) -> int:
+        return int(self.start.size)
+
+    def genotype(self, candidate, support_reads: Iterable[str], options) -> Tuple[str, int, int]:
+        contig, start, end, kinds = candidate[0], int(candidate[1]), int(candidate[2]), candidate[3]
+        lo_q, hi_q = max(0, start - 1000), min(self.contig_length, end + 1000)
+        alt = set(support_reads)
+        ref_no = 0
+        if len(self) and hi_q > lo_q:
+            lo = int(np.searchsorted(self._end_running_max, lo_q, side="right"))
+            hi = int(np.searchsorted(self.start, hi_q, side="left"))
+            if hi > lo:
+                sl = slice(lo, hi)
+                s, e, nid = self.start[sl], self.end[sl], self.name_id[sl]
+                usable = (e > lo_q) & ~self.skip[sl] & (self.mapq[sl] >= options.min_mapq)
+                alt_ids = [self._name_to_id[n] for n in alt if n in self._name_to_id]
+                if alt_ids:
+                    usable &= ~np.isin(nid, alt_ids)
+                pick = np.flatnonzero(usable)[:MAX_GENOTYPE_ALIGNMENTS]
+                s, e, nid = s[pick], e[pick], nid[pick]
+                if len(kinds) != 1:
+                    votes = np.ones(pick.size, dtype=bool)                           # genotype.py:56-57
+                elif kinds[0] in ("DEL", "INV"):                                     # genotype.py:46-50
+                    ov = min((end - start) / 2, 2000)
+                    votes = ((s < end - ov) & (e > end + 100)) | ((s < start - 100) & (e > start + ov))
+                elif kinds[0] in ("INS", "DUP"):                                     # genotype.py:52-54
+                    votes = (s < start - 100) & (e > end + 100)
+                else:
+                    votes = np.zeros(pick.size, dtype=bool)
+                ref_no = int(np.unique(nid[votes]).size)
+        alt_no = len(alt)
+        gt = "./."
+        if len(kinds) == 1 and alt_no + ref_no >= options.min_gt_depth:              # genotype.py:65-71
+            ratio = alt_no / (alt_no + ref_no)
+            if ratio >= options.homo_thresh:
+                gt = "1/1"
+            elif ratio >= options.hete_thresh:
+                gt = "0/1"
+            else:
+                gt = "0/0"
+        return gt, ref_no, alt_no
+
+
+    def genotype_many(self, candidates: Sequence, supports: Sequence[Iterable[str]], options) -> list:
+        """:meth:`genotype` for every candidate of a chromosome in one vectorised pass: the
+        (candidate, alignment) pairs of all windows are expanded side by side, filtered, capped at
+        500 usable alignments per candidate by a segmented running count, and the distinct
+        reference-supporting read names are counted per candidate."""
+        m = len(candidates)
+        if m == 0:
+            return []
+        start = np.array([int(c[1]) for c in candidates], dtype=np.int64)
+        end = np.array([int(c[2]) for c in candidates], dtype=np.int64)
+        # 0: several (or no) types -> every usable alignment votes; 1: DEL/INV; 2: INS/DUP; 3: no rule
+        rule = np.array([0 if len(c[3]) != 1 else 1 if c[3][0] in ("DEL", "INV") else 2 if c[3][0] in ("INS", "DUP") else 3
+                         for c in candidates], dtype=np.int64)
+        alts = [set(sup) for sup in supports]
+        ref_no = np.zeros(m, dtype=np.int64)
+        if len(self):
+            lo_q, hi_q = np.maximum(0, start - 1000), np.minimum(self.contig_length, end + 1000)
+            lo = np.searchsorted(self._end_running_max, lo_q, side="right")
+            hi = np.searchsorted(self.start, hi_q, side="left")
+            cnt = np.where(hi_q > lo_q, np.maximum(hi - lo, 0), 0)
+            total = int(cnt.sum())
+            if total:
+                first = np.cumsum(cnt) - cnt                               # pair index where each candidate begins
+                cand = np.repeat(np.arange(m), cnt)
+                pos = np.arange(total) - np.repeat(first, cnt) + np.repeat(lo, cnt)
+                s, e, nid = self.start[pos], self.end[pos], self.name_id[pos]
+                usable = (e > lo_q[cand]) & ~self.skip[pos] & (self.mapq[pos] >= options.min_mapq)
+                n_names = len(self._name_to_id)
+                key = cand * n_names + nid
+                alt_key = [j * n_names + self._name_to_id[nm] for j, a in enumerate(alts) for nm in a
+                           if nm in self._name_to_id]
+                if alt_key:
+                    usable &= ~np.isin(key, np.array(alt_key, dtype=np.int64))
+                running = np.cumsum(usable)
+                before = np.repeat(np.where(cnt > 0, running[np.minimum(first, total - 1)] - usable[np.minimum(first, total - 1)], 0), cnt)
+                pick = usable & (running - before <= MAX_GENOTYPE_ALIGNMENTS)
+                st, en, r = start[cand], end[cand], rule[cand]
+                ov = np.minimum((en - st) / 2, 2000)
+                votes = np.where(r == 0, True,
+                                 np.where(r == 1, ((s < en - ov) & (e > en + 100)) | ((s < st - 100) & (e > st + ov)),
+                                          np.where(r == 2, (s < st - 100) & (e > en + 100), False)))
+                distinct = np.unique(key[pick & votes])
+                ref_no = np.bincount(distinct // n_names, minlength=m)
+        out = []
+        for j in range(m):
+            alt_no, rn = len(alts[j]), int(ref_no[j])
+            gt = "./."
+            if rule[j] != 0 and alt_no + rn >= options.min_gt_depth:
+                ratio = alt_no / (alt_no + rn)
+                gt = "1/1" if ratio >= options.homo_thresh else "0/1" if ratio >= options.hete_thresh else "0/0"
+            out.append((gt, rn, alt_no))
+        return out
+
+
+# ------------------------------------------------------------------------------------------------
+# VCF records of one region
+# ------------------------------------------------------------------------------------------------
+def region_records(candidates: list, region: str, read_names: dict, sig_types: Sequence[str],
+                   sig_scores: dict, class_scores: Sequence, mechanisms: dict, options,
+                   genotype: Callable) -> List[Tuple[object, str]]:
+    """``[(qual, vcf_line), ...]`` for one region (output.py:469-598).  ``genotype(candidate,
+    support_read_names, options) -> (GT, DR, DV)`` is :meth:`AlignmentTable.genotype` or the
+    reference's ``genotyper``.  ``qual`` keeps its Python/numpy type so ``str(qual)`` prints what the
+    reference prints into ``<chrom>.score.txt``."""
+    pending = pending_records(candidates, region, read_names, sig_types, sig_scores, class_scores, options)
+    return [(q, f"{head}\t{gt}:{dr}:{dv}") for (q, head, cand, names) in pending
+            for gt, dr, dv in (genotype(cand, names, options),)]
+
+
+def pending_records(candidates: list, region: str, read_names: dict, sig_types: Sequence[str],
+                    sig_scores: dict, class_scores: Sequence, options) -> list:
+    """Everything of a region's records except the genotype: ``[(qual, line_without_sample_column,
+    candidate, supporting_read_names), ...]``."""
+    if not candidates:
+        return []
+    mean_score = np.mean(class_scores)                                # float32 in, float32 out
+    class_penalty = (1 - round(mean_score, 2)) * 100                  # output.py:473-474
+    contig, start, end = region.split("+")[:3]
+    start, end = int(start), int(end)
+    counts = Counter(sig_types)                                       # output.py:525-529
+    flt = "Uncovered" if counts.get("sigUncovered", 0) >= 0.75 * len(sig_types) and "sigUncovered" in counts else "PASS"
+    out = []
+    for kinds_str, read_ids, bkps in candidates:
+        support = len(read_ids)
+        if support < options.min_support:                             # output.py:495-496
+            continue
+        names = [read_names[r] for r in read_ids]
+        spread = np.std([int(sig_scores[r]) for r in read_ids]) / support          # output.py:551
+        qual = min(100, spread + class_penalty)
+        kinds, kb = refine_types(kinds_str.split("+"), bkps, options.min_sv_size)
+        info = [f"END={end}", f"SVLEN={end - start}", "SVTYPE=" + "+".join(kinds), f"SUPPORT={support}",
+                "BKPS=" + ",".join(f"{k}:{b[2]}-{b[0]}-{b[1]}" for k, b in zip(kinds, kb))]
+        if options.qname:
+            info.append("READS=" + ",".join(names))
+        alt = "<CSV>" if len(kinds) >= 2 else "<SV>"                  # output.py:573-576
+        out.append((qual, "\t".join([contig, str(start), "0", "N", alt, str(qual), flt, ";".join(info), "GT:DR:DV"]),
+                    (contig, start, end, kinds), names))
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# whole chromosome
+# ------------------------------------------------------------------------------------------------
+def call_chromosome(table, labels: np.ndarray, probs: np.ndarray, options, genotype,
+                    aggregate: Callable = aggregate_region) -> List[Tuple[object, str]]:
+    """The per-row loop of ``Predict.run`` (predict.py:213-300) followed, region by region, by
+    aggregation and record assembly.  Returns ``[(qual, vcf_line), ...]`` in file order.
+
+    Row rules kept from the reference: a forward signature classified INV is dropped before it can
+    open a region (predict.py:229-231); a region is flushed when the *next kept* row names another
+    region (predict.py:235-247); a row of a non-main segment pair (id without ``m``) classified DEL
+    or INS still contributes its score and metadata but no call (predict.py:279-281); later rows
+    overwrite earlier ones with the same read id and class."""
+    assert probs.dtype == np.float32, "scores must stay numpy.float32 (SURVEY §8(b))"
+    n = len(table)
+    pred_arr = np.asarray(labels).astype(np.int64)
+    pred = pred_arr.tolist()
+    # round(np.float32, 2) of the winning class, elementwise the same ufunc as numpy.round
+    win = np.round(probs[np.arange(n), pred_arr], 2) if n else np.zeros(0, np.float32)
+    fwd_inv = ((table.forward == "True") & (pred_arr == 2)).tolist() if n else []
+    read_num, region_col, read_name = table.read_num.tolist(), table.region.tolist(), table.read_name.tolist()
+    sig_type, sig_score, mech = table.sig_type.tolist(), table.sig_score.tolist(), table.mechanism.tolist()
+    b0, b1, b2 = table.bkp_start.tolist(), table.bkp_end.tolist(), table.bkp_len.tolist()
+
+    records: list = []
+    reads: dict = {}
+    names: dict = {}
+    scores: dict = {}
+    mechs: dict = {}
+    types: list = []
+    wins: list = []
+    last = ""
+
+    def flush():
+        records.extend(pending_records(aggregate(reads), last, names, types, scores, wins, options))
+
+    for i in range(n):
+        if fwd_inv[i]:
+            continue
+        region = region_col[i]
+        if region != last:
+            if last != "":
+                flush()
+            last = region
+            reads, names, scores, mechs, types, wins = {}, {}, {}, {}, [], []
+        rn = read_num[i]
+        main = "m" in rn
+        key = rn.replace("m", "") if main else rn
+        names[key] = read_name[i]
+        types.append(sig_type[i])
+        wins.append(win[i])
+        scores[key] = sig_score[i]
+        mechs[key] = mech[i]
+        p = pred[i]
+        if not main and p < 2:
+            continue
+        slot = reads.get(key)
+        if slot is None:
+            reads[key] = {p: [b0[i], b1[i], b2[i]]}
+        else:
+            slot[p] = [b0[i], b1[i], b2[i]]
+    flush()                                                           # predict.py:298-300
+    if hasattr(genotype, "genotype_many"):
+        gts = genotype.genotype_many([r[2] for r in records], [r[3] for r in records], options)
+    else:
+        gts = [genotype(r[2], r[3], options) for r in records]
+    return [(q, f"{head}\t{gt}:{dr}:{dv}") for (q, head, _, _), (gt, dr, dv) in zip(records, gts)]
+
+
+def write_chromosome(out_path_prefix: str, records: List[Tuple[object, str]]) -> None:
+    """``<prefix>.vcf`` and ``<prefix>.score.txt`` as ``merge_split_vcfs`` (output.py:307) and
+    ``cal_scores_max_min`` (output.py:601-612) expect them."""
+    with open(out_path_prefix + ".vcf", "w") as vcf, open(out_path_prefix + ".score.txt", "w") as sc:
+        for qual, line in records:
+            sc.write(str(qual) + "\n")
+            vcf.write(line + "\n")

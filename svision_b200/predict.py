@@ -2,14 +2,19 @@
 
 ``run_predict`` parses the BED once (:mod:`svision_b200.bed`), classifies every row on the GPU in
 one call (:class:`svision_b200.classifier.Classifier`; the model is loaded once per process, not
-once per chromosome as ``predict.py:179-184`` does), then replays the reference's per-row
-bookkeeping (``predict.py:213-300``) unchanged in meaning and hands each finished region to the
-reference's own aggregation and VCF writer, which stay where they are:
+once per chromosome as ``predict.py:179-184`` does), then turns labels and scores into VCF records.
+Two ways, same text:
 
-    aggregate = Predict.get_region_potential_svtypes      (predict.py:29-145)
-    write     = src.network.output.write_results_to_vcf    (output.py:469-598)
+* default: :mod:`svision_b200.calls` -- this package's own per-row loop, region aggregation, type
+  refinement, record assembly and a genotyper that reads the BAM once per chromosome
+  (byte-identical to the reference's text on the golden stream);
+* injected: the reference's own functions stay where they are and are passed in,
 
-Both are *injected* so nothing of the reference is copied here; INTEGRATION.md shows the patch.
+      aggregate = Predict.get_region_potential_svtypes      (predict.py:29-145)
+      write     = src.network.output.write_results_to_vcf    (output.py:469-598)
+
+  with :func:`replay_rows` feeding them (INTEGRATION.md shows the patch).
+
 Output files are the reference's: ``<prefix>.vcf`` and ``<prefix>.score.txt`` (predict.py:157-158).
 """
 from __future__ import annotations
@@ -76,16 +81,32 @@ def replay_rows(table: "_bed.SegmentsTable", labels: np.ndarray, probs: np.ndarr
     return flushed + 1
 
 
-def run_predict(segments_out_file: str, out_path_prefix: str, options, aggregate: Callable,
-                write: Callable, classifier=None, chrom: Optional[str] = None) -> int:
+def run_predict(segments_out_file: str, out_path_prefix: str, options, aggregate: Callable = None,
+                write: Callable = None, classifier=None, chrom: Optional[str] = None, genotype=None) -> int:
     """Body of ``Predict.run``.  ``options`` is the reference's argparse namespace (uses
-    ``model_path``; ``batch_size`` is accepted and ignored: micro-batching is internal).
-    Errors propagate (the reference swallows them: ``SVision:306-309``)."""
+    ``model_path``, ``min_support``, ``min_sv_size``, ``qname``, ``bam_path``, ``min_mapq``,
+    ``min_gt_depth``, ``homo_thresh``, ``hete_thresh``; ``batch_size`` is accepted and ignored:
+    micro-batching is internal).  Errors propagate (the reference swallows them: ``SVision:306-309``).
+
+    Without ``aggregate``/``write`` the records come from :mod:`svision_b200.calls`; ``genotype`` is
+    then a :class:`calls.AlignmentTable`, a callable ``(candidate, read_names, options) -> (GT, DR, DV)``,
+    or None to load ``options.bam_path`` once for ``chrom`` (needs pysam, as the reference does).
+    Returns the number of regions flushed (injected mode) or of records written (default mode)."""
     table = _bed.read_segments_bed(segments_out_file)
     clf = classifier if classifier is not None else get_classifier(options.model_path)
     if chrom:
         logging.info("Predicting " + chrom)                           # predict.py:204
     labels, probs = clf.classify(table.rows)
+    if aggregate is None and write is None:
+        from . import calls
+        if genotype is None:
+            contig = chrom if chrom else (str(table.region[0]).split("+")[0] if len(table) else None)
+            genotype = calls.AlignmentTable.from_bam(options.bam_path, contig) if contig else (lambda *a: ("./.", 0, 0))
+        records = calls.call_chromosome(table, labels, probs, options, genotype)
+        calls.write_chromosome(out_path_prefix, records)
+        return len(records)
+    if aggregate is None or write is None:
+        raise ValueError("inject both of the reference's aggregate and write functions, or neither")
     with open(out_path_prefix + ".score.txt", "w") as score_out, \
             open(out_path_prefix + ".vcf", "w") as vcf_out:
 
@@ -101,15 +122,12 @@ class Predict:
     """Same constructor and ``run`` signature as the reference class (predict.py:14-27,148)."""
 
     def __init__(self, chrom, segments_out_file, aggregate: Callable = None, write: Callable = None,
-                 classifier=None):
+                 classifier=None, genotype=None):
         self.segments_out_file = segments_out_file
         self.chrom = chrom
         self.num_classes = 5
-        self._aggregate, self._write, self._classifier = aggregate, write, classifier
+        self._aggregate, self._write, self._classifier, self._genotype = aggregate, write, classifier, genotype
 
     def run(self, out_path_prefix, options):
-        if self._aggregate is None or self._write is None:
-            raise RuntimeError("Predict needs the reference's get_region_potential_svtypes and "
-                               "write_results_to_vcf injected (see INTEGRATION.md)")
         return run_predict(self.segments_out_file, out_path_prefix, options, self._aggregate,
-                           self._write, self._classifier, self.chrom)
+                           self._write, self._classifier, self.chrom, self._genotype)

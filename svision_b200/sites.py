@@ -126,3 +126,106 @@ def rows_to_bed_lines(rows: np.ndarray, region_size: int = 19) -> list[str]:
                 str(1000 * reg + 100), str(1000 * reg + 200), "0.5", f2, "NA", "100"]
         lines.append("\t".join(cols))
     return lines
+
+
+def make_region_table(n_rows: int, seed: int = SEED_CONFIG4, profile: str = "hifi", contig: str = "chr1"):
+    """Config-4 style stream: P1 rows grouped into synthetic regions of 19±8 rows
+    with the metadata columns the reference's per-row loop consumes (``src/network/predict.py:218-226``;
+    BED columns 13-22, writer ``src/collection/output_clusters.py:180-182,207-209``).  Every read has a
+    main row (id ``<k>m``); ≈12 % of reads add one or two rows of a main×minor pair (id ``<k>``),
+    ≈8 % of regions are mostly ``sigUncovered``.  Returns a :class:`svision_b200.bed.SegmentsTable`."""
+    from .bed import SegmentsTable
+    rng = np.random.default_rng(seed + 1)
+    rows = make_sites_p1(n_rows, seed=seed, profile=profile)
+    col = {k: [] for k in ("read_num", "region", "read_name", "sig_type", "bkp_start", "bkp_end",
+                           "sig_score", "forward", "mechanism", "bkp_len")}
+    pos, region_no, n = 100_000, 0, 0
+    mechanisms = ("None", "NHEJ+0", "NHEJ+1", "FoSTeS+2")
+    while n < n_rows:
+        size = int(np.clip(rng.normal(19, 8), 1, 60))
+        width = int(10 ** rng.uniform(1.7, 4.0))
+        start, end = pos, pos + width
+        region = f"{contig}+{start}+{end}+{int(rng.integers(10, 60))}"
+        uncovered = rng.random() < 0.08
+        base_len = int(rng.integers(50, width + 51))
+        k = 0
+        emitted = 0
+        while emitted < size and n < n_rows:
+            k += 1
+            name = f"m{region_no}/{k}/ccs"
+            score = int(rng.integers(0, 40))
+            n_minor = int(rng.choice([0, 1, 2], p=[0.88, 0.07, 0.05]))
+            for sub in range(1 + n_minor):
+                if emitted >= size or n >= n_rows:
+                    break
+                main = sub == 0
+                col["read_num"].append(f"{k}m" if main else f"{k}")
+                col["region"].append(region)
+                col["read_name"].append(name)
+                col["sig_type"].append("sigUncovered" if (uncovered and rng.random() < 0.85) else "sigGap")
+                jit = int(rng.integers(-6, 7))
+                col["bkp_start"].append(start + jit if main else start + int(rng.integers(0, width)))
+                col["bkp_end"].append(start + jit + 1 if main else end + int(rng.integers(-8, 9)))
+                col["sig_score"].append(str(score))
+                col["forward"].append("True" if (main or rng.random() < 0.4) else "False")
+                col["mechanism"].append(mechanisms[int(rng.integers(0, len(mechanisms)))])
+                col["bkp_len"].append(base_len + int(rng.integers(-3, 4)))
+                emitted += 1
+                n += 1
+        pos = end + int(rng.integers(2_000, 50_000))
+        region_no += 1
+    obj = lambda k: np.array(col[k], dtype=object)                                   # noqa: E731
+    i64 = lambda k: np.array(col[k], dtype=np.int64)                                 # noqa: E731
+    return SegmentsTable(rows=rows, read_num=obj("read_num"), region=obj("region"), read_name=obj("read_name"),
+                         sig_type=obj("sig_type"), bkp_start=i64("bkp_start"), bkp_end=i64("bkp_end"),
+                         sig_score=obj("sig_score"), forward=obj("forward"), mechanism=obj("mechanism"),
+                         bkp_len=i64("bkp_len"))
+
+
+def table_to_bed_lines(table) -> list[str]:
+    """23-column BED text of a :class:`SegmentsTable` (inverse of ``bed.read_segments_bed``)."""
+    r = table.rows
+    tf = ("False", "True")
+    return ["\t".join([str(table.region[i]), str(r[i, 0]), str(r[i, 1]), str(r[i, 2]), str(r[i, 3]), tf[int(r[i, 4] == 1)],
+                       str(r[i, 5]), str(r[i, 6]), str(r[i, 7]), str(r[i, 8]), tf[int(r[i, 9] == 1)],
+                       str(r[i, 10]), str(r[i, 11]), str(table.read_num[i]), "1", str(table.read_name[i]),
+                       str(table.sig_type[i]), str(table.bkp_start[i]), str(table.bkp_end[i]),
+                       str(table.sig_score[i]), str(table.forward[i]), str(table.mechanism[i]),
+                       str(table.bkp_len[i])]) for i in range(len(table))]
+
+
+def make_alignments(table, seed: int = 5, depth: int = 30, contig_length: int = 250_000_000):
+    """Synthetic coordinate-sorted alignments around the regions of ``table`` for the genotyping step
+    (reference ``src/network/genotype.py:17-73``): per region ``depth`` reads with random extents around
+    the window, the region's own supporting read names among them, and a few secondary / unmapped /
+    low-quality records.  Returns a dict of columns (``reference_start``, ``reference_end``,
+    ``mapping_quality``, ``is_unmapped``, ``is_secondary``, ``query_name``, ``contig_length``)."""
+    rng = np.random.default_rng(seed)
+    regions, first = np.unique(np.asarray(table.region, dtype=object).astype(str), return_index=True)
+    names_by_region: dict = {}
+    for reg, nm in zip(table.region.tolist(), table.read_name.tolist()):
+        names_by_region.setdefault(reg, []).append(nm)
+    s, e, q, u, sec, names = [], [], [], [], [], []
+    for reg in regions[np.argsort(first)].tolist():
+        _, a, b = reg.split("+")[:3]
+        a, b = int(a), int(b)
+        own = list(dict.fromkeys(names_by_region[reg]))
+        for j in range(depth):
+            left = a - int(rng.integers(-200, 6000))
+            right = b + int(rng.integers(-200, 6000))
+            if right <= left:
+                right = left + 50
+            s.append(max(0, left))
+            e.append(right)
+            q.append(int(rng.choice([0, 5, 20, 60], p=[0.05, 0.05, 0.2, 0.7])))
+            u.append(bool(rng.random() < 0.02))
+            sec.append(bool(rng.random() < 0.05))
+            # a third of the records belong to supporting reads (excluded from the reference count);
+            # some names repeat (supplementary pieces of one read)
+            names.append(own[int(rng.integers(0, len(own)))] if rng.random() < 0.33
+                         else f"bg{a}/{int(rng.integers(0, depth * 2 // 3))}")
+    order = np.argsort(np.array(s, dtype=np.int64), kind="stable")
+    take = lambda x, dt: np.array(x, dtype=dt)[order]                                # noqa: E731
+    return dict(reference_start=take(s, np.int64), reference_end=take(e, np.int64),
+                mapping_quality=take(q, np.int64), is_unmapped=take(u, bool), is_secondary=take(sec, bool),
+                query_name=take(names, object), contig_length=contig_length)

@@ -1,0 +1,170 @@
+"""Post-classification host step: ``svision_b200.calls`` against the text the
+reference's own functions print.
+
+* golden: ``tests/golden/calls_golden.npz`` holds the VCF / score text produced by the unmodified
+  ``get_region_potential_svtypes`` + ``write_results_to_vcf`` + ``genotyper`` (``oracle/make_calls_golden.py``)
+  on a seeded synthetic stream; ``calls.call_chromosome`` + ``calls.AlignmentTable`` must reproduce it
+  byte for byte (no reference tree needed -> also runs on the GPU box);
+* live (build container only): fuzz of each function against its reference counterpart."""
+import os
+import sys
+import types
+
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path.insert(0, ROOT)
+
+from oracle import make_calls_golden as G, reference_loader as RL   # noqa: E402
+from svision_b200 import calls, sites                                # noqa: E402
+
+needs_reference = pytest.mark.skipif(not RL.available(), reason="reference tree not present (GPU box)")
+
+
+@pytest.fixture(scope="module")
+def golden():
+    g = np.load(os.path.join(HERE, "golden", "calls_golden.npz"))
+    n_rows, table_seed, _label_seed, aln_seed = (int(v) for v in g["meta"])
+    table = sites.make_region_table(n_rows, seed=table_seed)
+    aln = sites.make_alignments(table, seed=aln_seed)
+    return g, table, aln
+
+
+def make_table(aln) -> calls.AlignmentTable:
+    return calls.AlignmentTable(aln["contig_length"], aln["reference_start"], aln["reference_end"],
+                                aln["mapping_quality"], aln["is_unmapped"], aln["is_secondary"], aln["query_name"])
+
+
+def render(records):
+    return ("".join(line + "\n" for _, line in records), "".join(str(q) + "\n" for q, _ in records))
+
+
+@pytest.mark.parametrize("tag,opt", [("s3_qname", G.options(3, True)), ("s1", G.options(1, False)),
+                                     ("s5_min200", G.options(5, False, 200))])
+def test_call_chromosome_reproduces_reference_text(golden, tag, opt):
+    g, table, aln = golden
+    at = make_table(aln)
+    for genotype in (at, at.genotype):            # one vectorised pass / candidate by candidate
+        records = calls.call_chromosome(table, g["labels"], g["probs"], opt, genotype)
+        vcf, score = render(records)
+        assert len(records) > 100
+        assert vcf == str(g[f"{tag}_vcf"])
+        assert score == str(g[f"{tag}_score"])
+
+
+def test_write_chromosome_files(golden, tmp_path):
+    g, table, aln = golden
+    recs = calls.call_chromosome(table, g["labels"], g["probs"], G.options(3, True), make_table(aln).genotype)
+    calls.write_chromosome(str(tmp_path / "chr1.predict.s3"), recs)
+    assert open(tmp_path / "chr1.predict.s3.vcf").read() == str(g["s3_qname_vcf"])
+    assert open(tmp_path / "chr1.predict.s3.score.txt").read() == str(g["s3_qname_score"])
+
+
+def test_empty_and_degenerate_inputs():
+    table = sites.make_region_table(40, seed=3)
+    empty = type(table)(**{k: getattr(table, k)[:0] for k in table.__dataclass_fields__})
+    at = calls.AlignmentTable(1000, [], [], [], [], [], [])
+    assert calls.call_chromosome(empty, np.zeros(0, np.int32), np.zeros((0, 5), np.float32), G.options(), at.genotype) == []
+    # every row a forward signature classified INV -> everything dropped, nothing flushed (predict.py:229-231)
+    lab = np.full(len(table), 2, np.int32)
+    pr = np.full((len(table), 5), 0.1, np.float32)
+    pr[:, 2] = 0.6
+    fwd = type(table)(**{**{k: getattr(table, k) for k in table.__dataclass_fields__},
+                         "forward": np.array(["True"] * len(table), dtype=object)})
+    assert calls.call_chromosome(fwd, lab, pr, G.options(1), at.genotype) == []
+    assert calls.aggregate_region({}) == []
+    with pytest.raises(ValueError):
+        calls.AlignmentTable(1000, [5, 3], [9, 9], [60, 60], [0, 0], [0, 0], ["a", "b"])
+    with pytest.raises(AssertionError):
+        calls.call_chromosome(table, lab, pr.astype(np.float64), G.options(), at.genotype)
+
+
+def test_round_matches_python_round_on_float32():
+    """``call_chromosome`` rounds the winning scores in one ``numpy.round``; the reference rounds them one
+    by one with ``round(numpy.float32, 2)`` (predict.py:251).  Same values, same dtype."""
+    x = np.random.default_rng(0).random(200_000).astype(np.float32)
+    r = np.round(x, 2)
+    assert r.dtype == np.float32
+    for i in range(0, x.size, 37):
+        v = round(x[i], 2)
+        assert type(v) is np.float32 and v == r[i]
+
+
+# ------------------------------------------------------------------------------------------------
+# live cross-checks against the reference functions (build container only)
+# ------------------------------------------------------------------------------------------------
+@needs_reference
+def test_aggregate_region_fuzz_vs_reference():
+    rng = np.random.default_rng(1)
+    with RL.reference_modules() as ref:
+        pred = ref.Predict("chr1", "unused")
+        for _ in range(400):
+            reads = {}
+            for r in rng.permutation(int(rng.integers(1, 25))).tolist():
+                kinds = rng.choice(5, size=int(rng.integers(1, 4)), replace=False).tolist()
+                reads[str(r)] = {np.int64(k): [int(rng.integers(0, 250_000_000)), int(rng.integers(0, 250_000_000)),
+                                               int(rng.integers(0, 100_000))] for k in kinds}
+            import copy
+            assert calls.aggregate_region(copy.deepcopy(reads)) == pred.get_region_potential_svtypes(copy.deepcopy(reads))
+
+
+@needs_reference
+def test_refine_types_fuzz_vs_reference():
+    rng = np.random.default_rng(2)
+    import copy
+    with RL.reference_modules() as ref:
+        for _ in range(3000):
+            ids = sorted(rng.choice(5, size=int(rng.integers(1, 6)), replace=False).tolist())
+            kinds = [calls.TYPE_NAMES[k] for k in ids]
+            anchor = int(rng.integers(1000, 100000))
+            bk = [[anchor + int(rng.integers(-15, 16)), anchor + int(rng.integers(-15, 16)), int(rng.integers(0, 400))]
+                  for _ in kinds]
+            opt = types.SimpleNamespace(min_sv_size=int(rng.choice([0, 50, 200])))
+            want = ref.refine_type(copy.deepcopy(kinds), copy.deepcopy(bk), opt)
+            got = calls.refine_types(copy.deepcopy(kinds), copy.deepcopy(bk), opt.min_sv_size)
+            assert (list(got[0]), [list(b) for b in got[1]]) == (list(want[0]), [list(b) for b in want[1]])
+
+
+@needs_reference
+def test_genotype_fuzz_vs_reference():
+    table = sites.make_region_table(1500, seed=77)
+    aln = sites.make_alignments(table, seed=78, depth=45)
+    at = make_table(aln)
+    rng = np.random.default_rng(3)
+    names_all = sorted(set(table.read_name.tolist()))
+    with RL.reference_modules() as ref:
+        ref.genotype.pysam = RL.FakePysam(aln)
+        regions = list(dict.fromkeys(table.region.tolist()))
+        batch = []
+        for trial in range(300):
+            reg = regions[int(rng.integers(0, len(regions)))]
+            contig, a, b = reg.split("+")[:3]
+            a, b = int(a) + int(rng.integers(-50, 50)), int(b) + int(rng.integers(-50, 5000))
+            kinds = [["DEL"], ["INS"], ["INV"], ["DUP"], ["tDUP"], ["INS", "tDUP"], []][int(rng.integers(0, 7))]
+            support = [names_all[int(i)] for i in rng.integers(0, len(names_all), size=int(rng.integers(0, 12)))]
+            support += [n for r, n in zip(table.region.tolist(), table.read_name.tolist()) if r == reg][:int(rng.integers(0, 9))]
+            opt = types.SimpleNamespace(min_mapq=int(rng.choice([0, 10, 30])), min_gt_depth=int(rng.choice([1, 4, 20])),
+                                        homo_thresh=0.8, hete_thresh=0.2, bam_path="x")
+            cand = (contig, a, b, kinds)
+            want = ref.genotyper(cand, support, opt)
+            assert at.genotype(cand, support, opt) == want, (trial, cand)
+            batch.append((cand, support, opt, want))
+        for mapq in (0, 10, 30):                       # the batched pass shares one options object
+            sub = [b for b in batch if b[2].min_mapq == mapq and b[2].min_gt_depth == 4]
+            got = at.genotype_many([b[0] for b in sub], [b[1] for b in sub], sub[0][2])
+            assert got == [b[3] for b in sub]
+
+
+@needs_reference
+@pytest.mark.parametrize("seed", [11, 12])
+def test_call_chromosome_live_vs_reference(seed):
+    table = sites.make_region_table(2500, seed=seed, profile="ont")
+    labels, probs = G.synthetic_labels(table, seed + 100)
+    aln = sites.make_alignments(table, seed=seed + 200, depth=20)
+    opt = G.options(2, True, 50)
+    vcf, score, opens = G.reference_text(table, labels, probs, aln, opt)
+    got_vcf, got_score = render(calls.call_chromosome(table, labels, probs, opt, make_table(aln)))
+    assert got_vcf == vcf and got_score == score
+    assert opens == vcf.count("\n") > 50           # the reference re-opens the BAM once per record

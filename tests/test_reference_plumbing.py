@@ -25,27 +25,10 @@ pytestmark = pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "src", "netw
 
 @pytest.fixture(scope="module")
 def reference_modules():
-    saved_path, saved_mods = list(sys.path), dict(sys.modules)
-    sys.dont_write_bytecode = True
-    sys.path.insert(0, os.path.join(ROOT, "oracle", "pysam_stub"))
-    sys.path.insert(0, REF)
-    tf = types.ModuleType("tensorflow")
-    bs4 = types.ModuleType("bs4")
-    bs4.BeautifulSoup = object
-    el = types.ModuleType("bs4.element")
-    el.NavigableString = str
-    bs4.element = el
-    sys.modules.update({"tensorflow": tf, "bs4": bs4, "bs4.element": el})
-    import warnings
-    with warnings.catch_warnings():
-        warnings.simplefilter("ignore")
-        from src.network.predict import Predict as RefPredict
-        from src.network.output import write_results_to_vcf
-    yield RefPredict, write_results_to_vcf
-    sys.path[:] = saved_path
-    for k in list(sys.modules):
-        if k not in saved_mods:
-            del sys.modules[k]
+    sys.path.insert(0, ROOT)
+    from oracle import reference_loader as RL
+    with RL.reference_modules() as ref:
+        yield ref.Predict, ref.write_results_to_vcf
 
 
 def test_run_predict_with_reference_aggregation_and_vcf_writer(reference_modules, synthetic_weights, tmp_path):
@@ -81,3 +64,12 @@ def test_run_predict_with_reference_aggregation_and_vcf_writer(reference_modules
         assert int(info["END"]) >= int(rec[1]) and int(info["SUPPORT"]) >= 1
         assert set(info["SVTYPE"].split("+")) <= {"DEL", "INS", "INV", "DUP", "tDUP"}
         assert rec[8] == "GT:DR:DV" and len(rec[9].split(":")) == 3
+
+    # default mode: this package's own aggregation / records / one-pass genotyper (svision_b200.calls),
+    # BAM read once through the same pysam stand-in -> byte-identical files
+    prefix2 = str(tmp_path / "own" / "chr9.predict.s5")
+    os.makedirs(os.path.dirname(prefix2))
+    m = P.run_predict(bed_path, prefix2, opt, classifier=OracleClassifier(), chrom="chr9")
+    assert m == len(vcf)
+    assert open(prefix2 + ".vcf").read() == open(prefix + ".vcf").read()
+    assert open(prefix2 + ".score.txt").read() == open(prefix + ".score.txt").read()
