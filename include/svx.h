@@ -144,6 +144,25 @@ int svx_profile_read(svx_handle *h, float *ms_out, int64_t *launches_out, int re
 int64_t svx_launch_count(void);
 void svx_launch_count_reset(void);
 
+/* ---- host side: <chrom>.segments.all.bed -> packed rows (no GPU involved) -------------------------
+ * Replaces BatchGenerator.read_class_list (src/network/create_batch.py:29-61) and the token parsing
+ * of next_batch (create_batch.py:103-137).  `text` is the whole file (23 tab-separated columns per
+ * line, writer: src/collection/output_clusters.py:180-182,207-209); blank lines are skipped.
+ *   rows  [n][12] int32  columns 1-12 packed as above (strand tokens -> 0/1)
+ *   bkp   [n][3]  int64  columns 17, 18, 22 (breakpoint start, end, length: predict.py:222-224)
+ *   spans [n][7][2] int64 byte offset and length, within `text`, of columns 0 (region), 13 (read id),
+ *                        15 (qname), 16 (signature type), 19 (score), 20 (forward), 21 (mechanism)
+ *   flags [n]     int32  SVX_BED_FLAG_* below
+ * A malformed line fails the whole call (SVX_ERR_INVALID; the message names the line). */
+#define SVX_BED_SPANS 7
+#define SVX_BED_FLAG_MAIN 1         /* read id contains 'm': a main segment pair (predict.py:279) */
+#define SVX_BED_FLAG_FORWARD 2      /* column 20 == "True" (predict.py:229) */
+#define SVX_BED_FLAG_UNCOVERED 4    /* column 16 == "sigUncovered" (output.py:526) */
+#define SVX_BED_FLAG_SAME_REGION 8  /* column 0 equals the previous row's (predict.py:235) */
+int svx_bed_count_rows(const char *text, int64_t len, int64_t *n_rows);
+int svx_bed_parse(const char *text, int64_t len, int64_t n_rows, int32_t *rows, int64_t *bkp,
+                  int64_t *spans, int32_t *flags);
+
 int64_t svx_max_batch(const svx_handle *h);
 int svx_device(const svx_handle *h);
 const char *svx_last_error(void);

@@ -14,7 +14,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libsvx.so")
-SOURCES = ["encoder.cu", "front.cu", "gemm_tc.cu", "conv_tc.cu", "conv_tc2.cu", "cnn_aux.cu", "svx_api.cu"]
+SOURCES = ["encoder.cu", "front.cu", "gemm_tc.cu", "conv_tc.cu", "conv_tc2.cu", "cnn_aux.cu", "svx_api.cu",
+           "host_bed.cpp"]
 HEADERS = ["common.cuh", "kernels.h", "encoder_bitmap.cuh", os.path.join("..", "..", "include", "svx.h")]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 
@@ -44,7 +45,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         common += ["-Xptxas", "-v"]
     procs = []
     for src in SOURCES:
-        obj = os.path.join(bdir, src.replace(".cu", ".o"))
+        obj = os.path.join(bdir, os.path.splitext(src)[0] + ".o")
         objs.append(obj)
         cmd = [_nvcc(), *common, "-c", os.path.join(CSRC, src), "-o", obj]
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)))

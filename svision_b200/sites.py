@@ -176,10 +176,9 @@ def make_region_table(n_rows: int, seed: int = SEED_CONFIG4, profile: str = "hif
         region_no += 1
     obj = lambda k: np.array(col[k], dtype=object)                                   # noqa: E731
     i64 = lambda k: np.array(col[k], dtype=np.int64)                                 # noqa: E731
-    return SegmentsTable(rows=rows, read_num=obj("read_num"), region=obj("region"), read_name=obj("read_name"),
-                         sig_type=obj("sig_type"), bkp_start=i64("bkp_start"), bkp_end=i64("bkp_end"),
-                         sig_score=obj("sig_score"), forward=obj("forward"), mechanism=obj("mechanism"),
-                         bkp_len=i64("bkp_len"))
+    return SegmentsTable(rows, i64("bkp_start"), i64("bkp_end"), i64("bkp_len"), read_num=obj("read_num"),
+                         region=obj("region"), read_name=obj("read_name"), sig_type=obj("sig_type"),
+                         sig_score=obj("sig_score"), forward=obj("forward"), mechanism=obj("mechanism"))
 
 
 def table_to_bed_lines(table) -> list[str]:

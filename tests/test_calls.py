@@ -64,14 +64,15 @@ def test_write_chromosome_files(golden, tmp_path):
 
 def test_empty_and_degenerate_inputs():
     table = sites.make_region_table(40, seed=3)
-    empty = type(table)(**{k: getattr(table, k)[:0] for k in table.__dataclass_fields__})
+    empty = table.take(slice(0, 0))
     at = calls.AlignmentTable(1000, [], [], [], [], [], [])
     assert calls.call_chromosome(empty, np.zeros(0, np.int32), np.zeros((0, 5), np.float32), G.options(), at.genotype) == []
     # every row a forward signature classified INV -> everything dropped, nothing flushed (predict.py:229-231)
     lab = np.full(len(table), 2, np.int32)
     pr = np.full((len(table), 5), 0.1, np.float32)
     pr[:, 2] = 0.6
-    fwd = type(table)(**{**{k: getattr(table, k) for k in table.__dataclass_fields__},
+    fwd = type(table)(table.rows, table.bkp_start, table.bkp_end, table.bkp_len,
+                      **{**{k: getattr(table, k) for k in table.STRING_COLUMNS},
                          "forward": np.array(["True"] * len(table), dtype=object)})
     assert calls.call_chromosome(fwd, lab, pr, G.options(1), at.genotype) == []
     assert calls.aggregate_region({}) == []

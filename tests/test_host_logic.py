@@ -48,6 +48,48 @@ def test_bed_empty_and_malformed(tmp_path):
         bed.read_segments_bed(str(p))
 
 
+def test_bed_native_parser_matches_pandas_reader(tmp_path):
+    table = sites.make_region_table(5000, seed=9, profile="ont")
+    p = tmp_path / "c.bed"
+    p.write_text("\n".join(sites.table_to_bed_lines(table)) + "\n")
+    a, b = bed.read_segments_bed(str(p)), bed.read_segments_bed_pandas(str(p))
+    assert np.array_equal(a.rows, b.rows) and np.array_equal(a.rows, table.rows)
+    for k in ("bkp_start", "bkp_end", "bkp_len", "flags"):
+        assert np.array_equal(getattr(a, k), getattr(b, k)), k
+        assert np.array_equal(getattr(a, k), getattr(table, k)), k
+    for k in bed.SegmentsTable.STRING_COLUMNS:
+        assert getattr(a, k).tolist() == getattr(b, k).tolist() == getattr(table, k).tolist(), k
+    assert a.label_strings() == b.label_strings()
+    sub = a.take(slice(10, 20))
+    assert len(sub) == 10 and sub.read_name.tolist() == table.read_name[10:20].tolist()
+
+
+def test_bed_native_parser_edge_cases():
+    base = sites.table_to_bed_lines(sites.make_region_table(3, seed=1))
+    cols = base[0].split("\t")
+    # no trailing newline, blank lines, CRLF, extra columns, negative and signed numbers, UTF-8 read name
+    neg = list(cols)
+    neg[1], neg[3], neg[17] = "-12", "+7", "-5"
+    utf = list(cols)
+    utf[15] = "läs/1"
+    text = ("\n".join([base[0], "", base[1] + "\textra\tcolumns", "\t".join(neg)]) + "\r\n" + "\t".join(utf)).encode()
+    t = bed.parse_segments_bed(text)
+    assert len(t) == 4
+    assert t.rows[2, 0] == -12 and t.rows[2, 2] == 7 and t.bkp_start[2] == -5
+    assert t.bkp_len[2] == int(cols[22])                       # '\r' before the newline is tolerated, as int() does
+    assert t.read_name[3] == "läs/1" and t.read_name[0] == cols[15]
+    assert t.flags[1] & bed.FLAG_SAME_REGION and not t.flags[0] & bed.FLAG_SAME_REGION
+    for bad, what in ((1, "x12"), (3, "99999999999"), (17, ""), (22, "1.5"), (12, "1_000")):
+        broken = list(cols)
+        broken[bad] = what
+        with pytest.raises(ValueError, match="line 2"):
+            bed.parse_segments_bed((base[0] + "\n" + "\t".join(broken) + "\n").encode())
+    with pytest.raises(ValueError, match="23 tab-separated"):
+        bed.parse_segments_bed(b"\t".join([b"1"] * 22) + b"\n")
+    with pytest.raises(TypeError):
+        bed.parse_segments_bed("text, not bytes")
+
+
 def test_replay_rows_region_flush_and_rules(tmp_path):
     rows = sites.make_sites_p1(12, seed=2)
     lines = [l.split("\t") for l in sites.rows_to_bed_lines(rows, region_size=4)]
