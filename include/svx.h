@@ -163,6 +163,25 @@ int svx_bed_count_rows(const char *text, int64_t len, int64_t *n_rows);
 int svx_bed_parse(const char *text, int64_t len, int64_t n_rows, int32_t *rows, int64_t *bkp,
                   int64_t *spans, int32_t *flags);
 
+/* ---- host side: signatures -> packed rows, skipping the text BED (no GPU involved) ---------------
+ * Replaces Signature.get_segs_cords (src/collection/classes.py:72-117) + proc_one_sig / linearOrNot /
+ * cal_non_linear (src/collection/output_clusters.py:11-27,124-251) for all signatures of a chromosome.
+ *   sig_aln_off [n_sig+1]      alignments of signature s are aln[sig_aln_off[s] .. sig_aln_off[s+1])
+ *   aln         [n_aln][5]     ref_start, ref_end, q_start, q_end, is_reverse: the fields of
+ *                              `sorted_aligns` that get_segs_cords reads (absolute coordinates)
+ *   sig_bkp_off [n_sig+1]      breakpoints of signature s (pair k of a main x inner combination uses
+ *                              breakpoint k+1, a main pair breakpoint 0: output_clusters.py:173,199)
+ *   rows        [capacity][12] packed rows as above
+ *   meta        [capacity][5]  signature index, sub id (BED column 14), bit0 main pair | bit1 forward
+ *                              (column 20), index into the breakpoint array, non-linear score (column 19)
+ *   n_rows                     rows produced; with capacity 0 nothing is written and this is the count.
+ * A signature whose segments span no reference base is skipped, as the reference skips it. */
+#define SVX_ALN_FIELDS 5
+#define SVX_PAIR_META 5
+int svx_pairs_generate(int64_t n_sig, const int64_t *sig_aln_off, const int64_t *aln,
+                       const int64_t *sig_bkp_off, int64_t capacity, int32_t *rows, int64_t *meta,
+                       int64_t *n_rows);
+
 int64_t svx_max_batch(const svx_handle *h);
 int svx_device(const svx_handle *h);
 const char *svx_last_error(void);

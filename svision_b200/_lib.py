@@ -17,7 +17,7 @@ SYMBOLS = (
     "svx_classify", "svx_debug_activation", "svx_gemm_selftest", "svx_conv_selftest", "svx_debug_counters", "svx_set_profiling",
     "svx_profile_read", "svx_launch_count",
     "svx_launch_count_reset", "svx_max_batch", "svx_device", "svx_last_error", "svx_version",
-    "svx_bed_count_rows", "svx_bed_parse",
+    "svx_bed_count_rows", "svx_bed_parse", "svx_pairs_generate",
 )
 
 
@@ -75,6 +75,8 @@ def load() -> ctypes.CDLL:
     lib.svx_bed_count_rows.restype = i32
     lib.svx_bed_parse.argtypes = [vp, i64, i64, vp, vp, vp, vp]
     lib.svx_bed_parse.restype = i32
+    lib.svx_pairs_generate.argtypes = [i64, vp, vp, vp, i64, vp, vp, ctypes.POINTER(i64)]
+    lib.svx_pairs_generate.restype = i32
     lib.svx_max_batch.argtypes = [vp]
     lib.svx_max_batch.restype = i64
     lib.svx_device.argtypes = [vp]

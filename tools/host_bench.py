@@ -58,6 +58,24 @@ def main():
         assert vcf == "".join(l + "\n" for _, l in recs), "text differs from the reference's"
         out.update(reference_rows_per_s=round(a.rows / dr), reference_s=round(dr, 3), reference_bam_opens=opens,
                    speedup_lower_bound=round(dr / dt, 2))
+    # §8(f) #4: signatures -> packed rows
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_pairs_golden", os.path.join(ROOT, "oracle", "make_pairs_golden.py"))
+    PG = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(PG)
+    from svision_b200 import pairs
+    clusters = PG.synthetic_clusters(3, max(200, a.rows // 9))
+    sig = pairs.SignatureTable.from_clusters([PG.dict_to_cluster(d) for d in clusters], 2, 20000)
+    t = time.perf_counter()
+    tb = pairs.generate_pairs(sig)
+    dp = time.perf_counter() - t
+    out.update(pair_signatures=len(sig), pair_rows=len(tb), pairs_rows_per_s=round(len(tb) / dp))
+    if a.reference:
+        t = time.perf_counter()
+        ref_text = PG.reference_lines(clusters, 2, 20000)
+        drp = time.perf_counter() - t
+        assert ref_text == "".join(l + "\n" for l in pairs.to_bed_lines(tb))
+        out.update(reference_pairs_rows_per_s=round(len(tb) / drp))
     print(json.dumps(out))
 
 
