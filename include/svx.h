@@ -105,6 +105,42 @@ int svx_classify_device(svx_handle *h, const int32_t *rows_dev, int64_t n, int32
 int svx_classify(svx_handle *h, const int32_t *rows_host, int64_t n, int32_t *labels_host,
                  float *probs_host);
 
+/* What the reference consumes per row downstream of the path: predict_value[i] (argmax) and
+ * softmax_value[i][predict_value[i]] (src/network/predict.py:230,251). */
+typedef struct {
+    int32_t label;             /* 0 DEL, 1 INS, 2 INV, 3 DUP, 4 tDUP */
+    float score;               /* softmax of that class */
+} svx_call;
+
+/* svx_classify_device, returning only the 8-byte call per site (written by the fc8 kernel). */
+int svx_classify_device_calls(svx_handle *h, const int32_t *rows_dev, int64_t n, svx_call *calls_dev,
+                              void *stream);
+
+/* ---- multi-GPU result exchange ---------------------------------------------------
+ * The reference parallelises Step 2 with one process per chromosome and temp files
+ * (SVision:311-323); here sites shard contiguously over one process per GPU, and the only exchange
+ * is the per-site call.  svx_classify_exchange classifies this rank's shard and its fc8 kernel stores
+ * every call straight into the gathered buffer of EVERY rank (peer-mapped over NVLink via CUDA IPC)
+ * and publishes an epoch flag; a one-warp kernel then waits for the other ranks' flags.  No separate
+ * collective runs.  Setup: every rank creates an exchange, exports its 64-byte IPC handle, the
+ * handles are all-gathered by the caller (torch.distributed in svision_b200/sharded.py) and attached.
+ *   gathered_dev  device pointer to svx_call[world][sites_per_rank] (rank-major = file order for
+ *                 contiguous shards), valid once the work queued on `stream` has finished and until
+ *                 the next-but-one svx_classify_exchange (two buffers alternate).  Consume it on
+ *                 `stream` (or after synchronising) before calling again.
+ * All ranks must call svx_classify_exchange the same number of times.  A rank that does not show up
+ * within SVX_EXCHANGE_TIMEOUT_MS (default 5000) is reported by svx_exchange_status, which
+ * synchronises the device; the wait never hangs the GPU. */
+#define SVX_IPC_HANDLE_BYTES 64
+typedef struct svx_exchange svx_exchange;
+int svx_exchange_create(svx_handle *h, int rank, int world, int64_t sites_per_rank, svx_exchange **out);
+int svx_exchange_export(svx_exchange *x, void *ipc_handle_out /* 64 bytes */);
+int svx_exchange_attach(svx_exchange *x, const void *ipc_handles /* [world][64], rank order */);
+int svx_classify_exchange(svx_handle *h, svx_exchange *x, const int32_t *rows_dev, int64_t n,
+                          const svx_call **gathered_dev, void *stream);
+int svx_exchange_status(svx_exchange *x);
+void svx_exchange_destroy(svx_exchange *x);
+
 /* Parity/debug: copy the activation named `name` of the LAST micro-batch (first `n` sites) to
  * host as float32, NHWC, valid positions only.  Names: "conv1" [55][55][96], "norm1"
  * [27][27][96], "conv2" [27][27][256], "norm2" [13][13][256], "conv3"/"conv4" [13][13][384],

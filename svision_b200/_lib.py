@@ -18,7 +18,10 @@ SYMBOLS = (
     "svx_profile_read", "svx_launch_count",
     "svx_launch_count_reset", "svx_max_batch", "svx_device", "svx_last_error", "svx_version",
     "svx_bed_count_rows", "svx_bed_parse", "svx_pairs_generate",
+    "svx_classify_device_calls", "svx_exchange_create", "svx_exchange_export", "svx_exchange_attach",
+    "svx_classify_exchange", "svx_exchange_status", "svx_exchange_destroy",
 )
+IPC_HANDLE_BYTES = 64
 
 
 class SvxWeights(ctypes.Structure):
@@ -77,6 +80,20 @@ def load() -> ctypes.CDLL:
     lib.svx_bed_parse.restype = i32
     lib.svx_pairs_generate.argtypes = [i64, vp, vp, vp, i64, vp, vp, ctypes.POINTER(i64)]
     lib.svx_pairs_generate.restype = i32
+    lib.svx_classify_device_calls.argtypes = [vp, vp, i64, vp, vp]
+    lib.svx_classify_device_calls.restype = i32
+    lib.svx_exchange_create.argtypes = [vp, i32, i32, i64, ctypes.POINTER(vp)]
+    lib.svx_exchange_create.restype = i32
+    lib.svx_exchange_export.argtypes = [vp, vp]
+    lib.svx_exchange_export.restype = i32
+    lib.svx_exchange_attach.argtypes = [vp, vp]
+    lib.svx_exchange_attach.restype = i32
+    lib.svx_classify_exchange.argtypes = [vp, vp, vp, i64, ctypes.POINTER(vp), vp]
+    lib.svx_classify_exchange.restype = i32
+    lib.svx_exchange_status.argtypes = [vp]
+    lib.svx_exchange_status.restype = i32
+    lib.svx_exchange_destroy.argtypes = [vp]
+    lib.svx_exchange_destroy.restype = None
     lib.svx_max_batch.argtypes = [vp]
     lib.svx_max_batch.restype = i64
     lib.svx_device.argtypes = [vp]

@@ -137,6 +137,19 @@ class Classifier:
             logits.data_ptr() if want_logits else None, self._stream()), "svx_classify_device")
         return (labels, probs, logits) if want_logits else (labels, probs)
 
+    def classify_device_calls(self, rows: torch.Tensor, raw: bool = False):
+        """Fused path returning only what ``predict.py:230,251`` consumes per row: (labels int32[N],
+        scores float32[N]) -- views of one ``svx_call[N]`` buffer the fc8 kernel writes
+        (``raw=True``: that buffer itself, int32[N,2] with the score bit-cast in column 1)."""
+        assert rows.dtype == torch.int32 and rows.is_contiguous() and rows.device == self.torch_device
+        n = rows.shape[0]
+        calls = torch.empty((n, 2), dtype=torch.int32, device=self.torch_device)
+        _lib.check(self._lib.svx_classify_device_calls(self._h, rows.data_ptr(), n, calls.data_ptr(),
+                                                       self._stream()), "svx_classify_device_calls")
+        if raw:
+            return calls
+        return calls[:, 0], calls[:, 1].view(torch.float32)
+
     def classify(self, rows, labels_out: Optional[np.ndarray] = None,
                  probs_out: Optional[np.ndarray] = None):
         """HOST entry (the call a reference-side user makes): rows numpy int32[N,12] ->

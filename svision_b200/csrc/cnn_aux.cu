@@ -107,46 +107,100 @@ __global__ void __launch_bounds__(256) pool_kernel(const PoolParams p, long long
     }
 }
 
-// One warp per site.
+// One warp per site, 8 sites per CTA.  Besides labels / probs / logits the kernel can emit the
+// 8-byte (label, score) call of every site -- what src/network/predict.py:230,251 consumes -- into
+// up to CALL_MAX_SINKS destinations: the local buffer and, in a multi-GPU exchange, the gathered
+// buffer of EVERY rank (peer-mapped memory written over NVLink, 64 contiguous bytes per CTA and
+// sink).  With `done` set, the last CTA to finish publishes `epoch` to each rank's flag word
+// (release, system scope): fc8 + softmax + argmax + all-gather + signal are this one kernel.
 __global__ void __launch_bounds__(256)
 fc8_softmax_kernel(const __half* __restrict__ x_hi, const __half* __restrict__ x_lo,
                    const float* __restrict__ w8, const float* __restrict__ b8, long long n,
                    int32_t* __restrict__ labels, float* __restrict__ probs,
-                   float* __restrict__ logits) {
+                   float* __restrict__ logits, const CallSinks sinks) {
+    __shared__ int2 call_s[8];
+    __shared__ int is_last;
     const int lane = threadIdx.x & 31;
-    const long long site = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
-    if (site >= n) return;
-    const __half* xh = x_hi + site * 4096;
-    const __half* xl = x_lo + site * 4096;
-    float acc[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
-    for (int i = 0; i < 128; ++i) {
-        const int k = lane + 32 * i;
-        const float x = __half2float(xh[k]) + __half2float(xl[k]);
-        const float* w = w8 + k * 5;
+    const int warp = threadIdx.x >> 5;
+    const long long site0 = (long long)blockIdx.x * 8;
+    const long long site = site0 + warp;
+    if (site < n) {
+        const __half* xh = x_hi + site * 4096;
+        const __half* xl = x_lo + site * 4096;
+        float acc[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+        for (int i = 0; i < 128; ++i) {
+            const int k = lane + 32 * i;
+            const float x = __half2float(xh[k]) + __half2float(xl[k]);
+            const float* w = w8 + k * 5;
 #pragma unroll
-        for (int j = 0; j < 5; ++j) acc[j] = fmaf(x, __ldg(w + j), acc[j]);
+            for (int j = 0; j < 5; ++j) acc[j] = fmaf(x, __ldg(w + j), acc[j]);
+        }
+#pragma unroll
+        for (int j = 0; j < 5; ++j)
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], off);
+        if (lane == 0) {
+            float l[5], mx = -CUDART_INF_F;
+            int arg = 0;
+#pragma unroll
+            for (int j = 0; j < 5; ++j) {
+                l[j] = acc[j] + b8[j];
+                if (l[j] > mx) { mx = l[j]; arg = j; }       // first maximum, like tf.argmax
+            }
+            float e[5], sum = 0.f;
+#pragma unroll
+            for (int j = 0; j < 5; ++j) { e[j] = expf(l[j] - mx); sum += e[j]; }
+            if (labels) labels[site] = arg;
+            float score = 0.f;
+#pragma unroll
+            for (int j = 0; j < 5; ++j) {
+                const float pj = e[j] / sum;
+                if (probs) probs[site * 5 + j] = pj;
+                if (logits) logits[site * 5 + j] = l[j];
+                if (j == arg) score = pj;
+            }
+            call_s[warp] = make_int2(arg, __float_as_int(score));
+        }
     }
-#pragma unroll
-    for (int j = 0; j < 5; ++j)
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], off);
-    if (lane == 0) {
-        float l[5], mx = -CUDART_INF_F;
-        int arg = 0;
-#pragma unroll
-        for (int j = 0; j < 5; ++j) {
-            l[j] = acc[j] + b8[j];
-            if (l[j] > mx) { mx = l[j]; arg = j; }       // first maximum, like tf.argmax
-        }
-        float e[5], s = 0.f;
-#pragma unroll
-        for (int j = 0; j < 5; ++j) { e[j] = expf(l[j] - mx); s += e[j]; }
-        labels[site] = arg;
-#pragma unroll
-        for (int j = 0; j < 5; ++j) {
-            probs[site * 5 + j] = e[j] / s;
-            if (logits) logits[site * 5 + j] = l[j];
-        }
+    if (sinks.count == 0) return;                          // uniform over the grid
+    __syncthreads();
+    {   // thread t -> sink t / 8, site t % 8: every sink receives one 64-byte run per CTA
+        const int r = threadIdx.x >> 3, i = threadIdx.x & 7;
+        if (r < sinks.count && site0 + i < n) sinks.ptr[r][site0 + i] = call_s[i];
+    }
+    if (sinks.done == nullptr) return;
+    __threadfence_system();                                // this thread's peer stores are performed
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int prev = atomicAdd(sinks.done, 1u);
+        is_last = prev + 1 == gridDim.x;
+        if (is_last) *sinks.done = 0;                      // ready for the next launch
+    }
+    __syncthreads();
+    if (is_last) {
+        __threadfence_system();
+        if (threadIdx.x < sinks.count)
+            asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(sinks.flag[threadIdx.x]), "l"(sinks.epoch)
+                         : "memory");
+    }
+}
+
+// One thread per rank waits until that rank's calls have landed in the local gathered buffer
+// (its fc8 kernel has published `epoch`).  Bounded: after `timeout_ns` the rank is reported in
+// *error (1 + rank) and the kernel exits instead of hanging the device.
+__global__ void exchange_wait_kernel(const unsigned long long* __restrict__ my_flags, int world,
+                                     unsigned long long epoch, unsigned long long timeout_ns,
+                                     unsigned int* __restrict__ error) {
+    const int r = threadIdx.x;
+    if (r >= world) return;
+    unsigned long long t0, now, v;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    for (;;) {
+        asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(my_flags + r) : "memory");
+        if (v >= epoch) break;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+        if (now - t0 > timeout_ns) { atomicExch(error, 1u + (unsigned)r); break; }
+        __nanosleep(200);
     }
 }
 
@@ -205,11 +259,20 @@ int launch_pool(const PoolParams& p, long long n_img, int num_sms, cudaStream_t 
 
 int launch_fc8_softmax(const __half* x_hi, const __half* x_lo, const float* w8, const float* b8,
                        long long n, int32_t* labels, float* probs, float* logits,
-                       cudaStream_t stream) {
+                       const CallSinks& sinks, cudaStream_t stream) {
     if (n <= 0) return 0;
+    if (sinks.count < 0 || sinks.count > CALL_MAX_SINKS) return fail(-1, "fc8: bad sink count");
     fc8_softmax_kernel<<<(unsigned)((n + 7) / 8), 256, 0, stream>>>(x_hi, x_lo, w8, b8, n, labels,
-                                                                     probs, logits);
+                                                                     probs, logits, sinks);
     SVX_LAUNCH_CHECK("fc8_softmax_kernel");
+    return 0;
+}
+
+int launch_exchange_wait(const unsigned long long* my_flags, int world, unsigned long long epoch,
+                         unsigned long long timeout_ns, unsigned int* error, cudaStream_t stream) {
+    if (world < 1 || world > CALL_MAX_SINKS) return fail(-1, "exchange: bad world size");
+    exchange_wait_kernel<<<1, 32, 0, stream>>>(my_flags, world, epoch, timeout_ns, error);
+    SVX_LAUNCH_CHECK("exchange_wait_kernel");
     return 0;
 }
 

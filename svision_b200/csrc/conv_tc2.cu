@@ -68,14 +68,19 @@ conv_tc2_kernel(const __grid_constant__ GemmLayer L) {
     constexpr int B_PLANE_BYTES = HALF_N * BLOCK_K * 2;
     constexpr bool A_LO = PASSES == 3;
     constexpr bool B_LO = PASSES >= 2;
-    constexpr int ACC_STRIDE = 256;                            // TMEM columns per buffer
+    // TMEM accumulator ring: tiles of <= 128 columns get four buffers, so the MMA warp can run four
+    // K = 256 chunks ahead of the epilogue (its per-tile store phase is the longest for the
+    // small-K layers: conv2 has only 20 k-blocks per 256 x 128 fp32 tile)
+    // (L.acc_bufs: 2 or 4; 4 only where the tile fits 128 TMEM columns)
+    const int NUM_ACC = (BLOCK_N <= 128 && L.acc_bufs == 4) ? 4 : 2;
+    const int ACC_STRIDE = TMEM_COLS / NUM_ACC;                // TMEM columns per buffer
     constexpr int COLS_PER_THREAD = BLOCK_N / 2;               // epilogue: column half per warp set
     static_assert(BLOCK_N % 32 == 0 && BLOCK_N <= 256, "BLOCK_N");
     static_assert(B_PLANE_BYTES % 1024 == 0, "weight half-tile must be whole swizzle atoms");
     extern __shared__ uint8_t smem_raw[];
     __shared__ uint64_t full_s[MAX_SLAB_SLOTS], empty_s[MAX_SLAB_SLOTS];
     __shared__ uint64_t full_b[MAX_B_STAGES], empty_b[MAX_B_STAGES];
-    __shared__ uint64_t tmem_full_bar[2], tmem_empty_bar[2];
+    __shared__ uint64_t tmem_full_bar[4], tmem_empty_bar[4];
     __shared__ uint32_t tmem_base_smem;
     __shared__ float bias_s[BLOCK_N];
 
@@ -107,7 +112,7 @@ conv_tc2_kernel(const __grid_constant__ GemmLayer L) {
         tma_prefetch_desc(&L.tm_b_lo);
         for (int s = 0; s < MAX_SLAB_SLOTS; ++s) { mbar_init(&full_s[s], 1); mbar_init(&empty_s[s], 1); }
         for (int s = 0; s < MAX_B_STAGES; ++s) { mbar_init(&full_b[s], 1); mbar_init(&empty_b[s], 1); }
-        for (int b = 0; b < 2; ++b) {
+        for (int b = 0; b < 4; ++b) {
             mbar_init(&tmem_full_bar[b], 1);
             mbar_init(&tmem_empty_bar[b], 16);        // 8 epilogue warps x 2 CTAs (leader's copy is used)
         }
@@ -222,8 +227,7 @@ conv_tc2_kernel(const __grid_constant__ GemmLayer L) {
                         if (++stage == L.n_b_stages) { stage = 0; phase ^= 1u; }
                         if (chunk_end) {
                             in_chunk = 0;
-                            acc ^= 1;
-                            if (acc == 0) acc_phase ^= 1u;
+                            if (++acc == NUM_ACC) { acc = 0; acc_phase ^= 1u; }
                         } else {
                             ++in_chunk;
                         }
@@ -278,8 +282,7 @@ conv_tc2_kernel(const __grid_constant__ GemmLayer L) {
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive_cluster(&tmem_empty_bar[acc], 0);    // leader's barrier
-                acc ^= 1;
-                if (acc == 0) acc_phase ^= 1u;
+                if (++acc == NUM_ACC) { acc = 0; acc_phase ^= 1u; }
                 if (DBG) c_epi_drain += clock64() - t1;
             }
             if (DBG) t0 = clock64();
@@ -516,6 +519,7 @@ int plan_slab_pair(GemmLayer& L) {
     if (nb > MAX_B_STAGES) nb = MAX_B_STAGES;
     if (nb < 2) return fail(-1, "conv2: shared memory budget too small for this layer");
     L.n_b_stages = nb;
+    L.acc_bufs = L.block_n <= 128 ? 4 : 2;
     L.use_slab = 2;
     return 0;
 }

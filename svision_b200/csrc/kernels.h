@@ -69,6 +69,7 @@ struct GemmLayer {
     int slab_rows;             // multiple of 8, >= 128 + max(row_off) - min(row_off), <= 256
     int off_min;               // min(row_off)
     int n_slab_slots, n_b_stages;
+    int acc_bufs;              // pair kernel: TMEM accumulator buffers (2, or 4 when block_n <= 128)
     int stage_cols;            // pair kernel: epilogue staging width (32, or 16 to free smem for weight stages)
     int desc_base_offset_mode; // 1: descriptor base_offset = (addr >> 7) & 7 for shifted starts
     // optional cycle counters (development): 8 x unsigned long long, atomically accumulated per CTA
@@ -109,10 +110,25 @@ struct PoolParams {
 };
 int launch_pool(const PoolParams& p, long long n_img, int num_sms, cudaStream_t stream);
 
-// logits = (x_hi + x_lo) @ W8 + b8 ; labels = argmax ; probs = softmax   (fp32, CUDA cores)
+// Destinations of the per-site (label, score) calls written by the fc8 kernel: the local buffer
+// and/or every rank's gathered buffer (peer-mapped), plus the completion signal of an exchange.
+constexpr int CALL_MAX_SINKS = 16;
+struct CallSinks {
+    int2* ptr[CALL_MAX_SINKS];                 // where site 0 of THIS launch goes in each sink
+    int count;                                 // 0: no calls are written
+    unsigned long long* flag[CALL_MAX_SINKS];  // word to publish `epoch` to, per sink (with `done`)
+    unsigned long long epoch;
+    unsigned int* done;                        // CTA completion counter (local); nullptr: no signal
+};
+
+// logits = (x_hi + x_lo) @ W8 + b8 ; labels = argmax ; probs = softmax   (fp32, CUDA cores);
+// labels / probs / logits may each be nullptr
 int launch_fc8_softmax(const __half* x_hi, const __half* x_lo, const float* w8 /*[4096][5]*/,
                        const float* b8, long long n, int32_t* labels, float* probs, float* logits,
-                       cudaStream_t stream);
+                       const CallSinks& sinks, cudaStream_t stream);
+// waits (bounded) until every rank has published `epoch` in my_flags[0..world)
+int launch_exchange_wait(const unsigned long long* my_flags, int world, unsigned long long epoch,
+                         unsigned long long timeout_ns, unsigned int* error, cudaStream_t stream);
 
 // NHWC [n][227][227][3] (fp32 or fp16) -> conv1 operand layout [n][57*57][64] fp16
 int launch_nhwc_to_s2d(const void* images, int dtype, long long n, __half* out, cudaStream_t stream);

@@ -114,6 +114,28 @@ struct svx_handle {
     long long prof_launches[SVX_PROFILE_SLOTS] = {};
 };
 
+// Multi-GPU result exchange (include/svx.h): the local gathered buffer, peer mappings of every
+// other rank's buffer (CUDA IPC), epoch-parity double buffering.
+struct svx_exchange {
+    svx_handle* h = nullptr;
+    int device = 0;                                 // copy: destroy must not touch a freed handle
+    int rank = 0, world = 1;
+    long long per_rank = 0;
+    void* local = nullptr;                          // cudaMalloc: [flags 256 B][region 0][region 1]
+    void* base[CALL_MAX_SINKS] = {};                // base[r]: rank r's buffer as mapped here
+    bool opened[CALL_MAX_SINKS] = {};
+    bool attached = false;
+    unsigned int* done = nullptr;                   // fc8 CTA counter
+    unsigned int* error = nullptr;                  // wait-kernel timeout report
+    unsigned long long epoch = 0;
+    unsigned long long timeout_ns = 5000000000ull;  // SVX_EXCHANGE_TIMEOUT_MS overrides
+    size_t region_bytes() const { return (size_t)world * (size_t)per_rank * sizeof(svx_call); }
+    char* region(int r, int parity) const {
+        return static_cast<char*>(base[r]) + 256 + (size_t)parity * region_bytes();
+    }
+    unsigned long long* flags(int r) const { return static_cast<unsigned long long*>(base[r]); }
+};
+
 namespace {
 
 struct DeviceGuard {
@@ -257,6 +279,7 @@ int setup_layer(svx_handle* h, int li, const __half* a_hi, const __half* a_lo, l
     if (h->use_slab && h->use_pair && s.block_n_pair > 0) {
         L.block_n = s.block_n_pair;
         if ((rc = plan_slab_pair(L))) return rc;
+        if (const char* e = std::getenv("SVX_ACC")) L.acc_bufs = std::atoi(e);   // development A/B
         L.desc_base_offset_mode = h->desc_bo_mode;
         a_box_rows = L.slab_rows;
         b_box_rows = L.block_n / 2;
@@ -347,7 +370,12 @@ int build_model(svx_handle* h, const svx_weights* w) {
 
     //                 layer    A hi      A lo      A rows  lda grid center out_f32 out_hi    out_lo   ldc  pos  vh  vw
     if ((rc = setup_layer(h, L_CONV1, h->x1, nullptr, B * P1, 64, S2D, 0, h->y1, nullptr, nullptr, 96, 0, 0, 0))) return rc;
-    if ((rc = setup_layer(h, L_CONV2, h->x2_hi, h->x2_lo, B * P2, h->x2_ld, G2, 2, h->y2, nullptr, nullptr, 256, 0, 0, 0))) return rc;
+    {   // SVX_Y2MASK=1 (development A/B): do not store conv2's outputs at pad positions (13 % of y2)
+        const char* e = std::getenv("SVX_Y2MASK");
+        const bool mask = e && std::atoi(e) != 0;
+        if ((rc = setup_layer(h, L_CONV2, h->x2_hi, h->x2_lo, B * P2, h->x2_ld, G2, 2, h->y2, nullptr, nullptr, 256,
+                              mask ? P2 : 0, mask ? 27 : 0, mask ? 27 : 0))) return rc;
+    }
     if ((rc = setup_layer(h, L_CONV3, h->x3_hi, h->x3_lo, B * P3, 256, G3, 1, nullptr, h->x4_hi, h->x4_lo, 384, P3, 13, 13))) return rc;
     if ((rc = setup_layer(h, L_CONV4, h->x4_hi, h->x4_lo, B * P3, 384, G3, 1, nullptr, h->x5_hi, h->x5_lo, 384, P3, 13, 13))) return rc;
     if ((rc = setup_layer(h, L_CONV5, h->x5_hi, h->x5_lo, B * P3, 384, G3, 1, h->y5, nullptr, nullptr, 256, 0, 0, 0))) return rc;
@@ -393,7 +421,7 @@ int profile_collect(svx_handle* h) {
 
 // x1 (conv1 operand) of `n` sites is resident -> labels / probs / logits
 int run_cnn(svx_handle* h, long long n, int32_t* labels, float* probs, float* logits,
-            cudaStream_t st, bool x2_ready = false) {
+            cudaStream_t st, bool x2_ready = false, const CallSinks* sinks = nullptr) {
     int rc;
     const long long rows[L_COUNT] = {n * P1, n * P2, n * P3, n * P3, n * P3, n, n};
     for (int li = 0; li < L_COUNT; ++li) h->layer[li].m_rows = rows[li];
@@ -436,7 +464,9 @@ int run_cnn(svx_handle* h, long long n, int32_t* labels, float* probs, float* lo
     mark(h, 10, st);
     if ((rc = run_layer(h, L_FC7, st))) return rc;
     mark(h, 11, st);
-    if ((rc = launch_fc8_softmax(h->x8_hi, h->x8_lo, h->w8, h->b8, n, labels, probs, logits, st))) return rc;
+    static const CallSinks no_sinks = {};
+    if ((rc = launch_fc8_softmax(h->x8_hi, h->x8_lo, h->w8, h->b8, n, labels, probs, logits,
+                                 sinks ? *sinks : no_sinks, st))) return rc;
     mark(h, -1, st);
     h->last_n = n;
     return 0;
@@ -631,6 +661,145 @@ int svx_classify(svx_handle* h, const int32_t* rows_host, int64_t n, int32_t* la
     SVX_CUDA_CHECK(cudaEventRecord(h->busy, st));
     SVX_CUDA_CHECK(cudaStreamSynchronize(st));
     return SVX_OK;
+}
+
+int svx_classify_device_calls(svx_handle* h, const int32_t* rows_dev, int64_t n, svx_call* calls_dev,
+                              void* stream) {
+    if (!h || !h->has_model) return fail(SVX_ERR_INVALID, "svx_classify_device_calls: handle has no model");
+    if (n < 0 || (n > 0 && (!rows_dev || !calls_dev)))
+        return fail(SVX_ERR_INVALID, "svx_classify_device_calls: bad arguments");
+    DeviceGuard guard(h->device);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    SVX_CUDA_CHECK(cudaStreamWaitEvent(st, h->busy, 0));
+    for (int64_t s = 0; s < n; s += h->max_batch) {
+        const int64_t m = n - s < h->max_batch ? n - s : h->max_batch;
+        int rc;
+        CallSinks sinks = {};
+        sinks.count = 1;
+        sinks.ptr[0] = reinterpret_cast<int2*>(calls_dev + s);
+        mark(h, 0, st);
+        if ((rc = encode_front(h, rows_dev + s * SVX_ROW_FIELDS, m, st))) return rc;
+        if ((rc = run_cnn(h, m, nullptr, nullptr, nullptr, st, h->use_front, &sinks))) return rc;
+    }
+    SVX_CUDA_CHECK(cudaEventRecord(h->busy, st));
+    return SVX_OK;
+}
+
+int svx_exchange_create(svx_handle* h, int rank, int world, int64_t sites_per_rank, svx_exchange** out) {
+    if (!out) return fail(SVX_ERR_INVALID, "svx_exchange_create: out is NULL");
+    *out = nullptr;
+    if (!h || !h->has_model) return fail(SVX_ERR_INVALID, "svx_exchange_create: handle has no model");
+    if (world < 1 || world > CALL_MAX_SINKS || rank < 0 || rank >= world || sites_per_rank <= 0)
+        return fail(SVX_ERR_INVALID, "svx_exchange_create: bad rank / world (<= 16) / sites_per_rank");
+    DeviceGuard guard(h->device);
+    std::unique_ptr<svx_exchange> x(new svx_exchange());
+    x->h = h; x->device = h->device; x->rank = rank; x->world = world; x->per_rank = sites_per_rank;
+    if (const char* e = std::getenv("SVX_EXCHANGE_TIMEOUT_MS")) {
+        const long long ms = std::atoll(e);
+        if (ms > 0) x->timeout_ns = (unsigned long long)ms * 1000000ull;
+    }
+    const size_t bytes = 256 + 2 * x->region_bytes();
+    // plain cudaMalloc (not a pool): the allocation is exported with cudaIpcGetMemHandle
+    cudaError_t e = cudaMalloc(&x->local, bytes);
+    if (e != cudaSuccess) return fail(SVX_ERR_NOMEM, std::string("svx_exchange_create: ") + cudaGetErrorString(e));
+    auto cleanup = [&](int rc) { cudaFree(x->local); cudaFree(x->done); return rc; };
+    if ((e = cudaMemset(x->local, 0, bytes)) != cudaSuccess ||
+        (e = cudaMalloc(reinterpret_cast<void**>(&x->done), 2 * sizeof(unsigned int))) != cudaSuccess ||
+        (e = cudaMemset(x->done, 0, 2 * sizeof(unsigned int))) != cudaSuccess ||
+        (e = cudaDeviceSynchronize()) != cudaSuccess)
+        return cleanup(fail(SVX_ERR_CUDA, std::string("svx_exchange_create: ") + cudaGetErrorString(e)));
+    x->error = x->done + 1;
+    x->base[rank] = x->local;
+    x->attached = world == 1;
+    *out = x.release();
+    return SVX_OK;
+}
+
+int svx_exchange_export(svx_exchange* x, void* ipc_handle_out) {
+    if (!x || !ipc_handle_out) return fail(SVX_ERR_INVALID, "svx_exchange_export: bad arguments");
+    static_assert(sizeof(cudaIpcMemHandle_t) == SVX_IPC_HANDLE_BYTES, "IPC handle size");
+    DeviceGuard guard(x->device);
+    cudaIpcMemHandle_t hd;
+    SVX_CUDA_CHECK(cudaIpcGetMemHandle(&hd, x->local));
+    std::memcpy(ipc_handle_out, &hd, sizeof(hd));
+    return SVX_OK;
+}
+
+int svx_exchange_attach(svx_exchange* x, const void* ipc_handles) {
+    if (!x || !ipc_handles) return fail(SVX_ERR_INVALID, "svx_exchange_attach: bad arguments");
+    if (x->attached) return fail(SVX_ERR_INVALID, "svx_exchange_attach: already attached");
+    DeviceGuard guard(x->device);
+    for (int r = 0; r < x->world; ++r) {
+        if (r == x->rank) continue;
+        cudaIpcMemHandle_t hd;
+        std::memcpy(&hd, static_cast<const char*>(ipc_handles) + (size_t)r * SVX_IPC_HANDLE_BYTES, sizeof(hd));
+        cudaError_t e = cudaIpcOpenMemHandle(&x->base[r], hd, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess)
+            return fail(SVX_ERR_CUDA, "svx_exchange_attach: cudaIpcOpenMemHandle(rank " + std::to_string(r) +
+                                          "): " + cudaGetErrorString(e));
+        x->opened[r] = true;
+    }
+    x->attached = true;
+    return SVX_OK;
+}
+
+int svx_classify_exchange(svx_handle* h, svx_exchange* x, const int32_t* rows_dev, int64_t n,
+                          const svx_call** gathered_dev, void* stream) {
+    if (!h || !h->has_model || !x || x->h != h) return fail(SVX_ERR_INVALID, "svx_classify_exchange: bad handle");
+    if (!x->attached) return fail(SVX_ERR_INVALID, "svx_classify_exchange: exchange is not attached");
+    if (n <= 0 || n > x->per_rank || !rows_dev)
+        return fail(SVX_ERR_INVALID, "svx_classify_exchange: need 0 < n <= sites_per_rank (pad the shard)");
+    DeviceGuard guard(h->device);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    SVX_CUDA_CHECK(cudaStreamWaitEvent(st, h->busy, 0));
+    const unsigned long long epoch = ++x->epoch;
+    const int parity = (int)(epoch & 1ull);
+    for (int64_t s = 0; s < n; s += h->max_batch) {
+        const int64_t m = n - s < h->max_batch ? n - s : h->max_batch;
+        int rc;
+        CallSinks sinks = {};
+        sinks.count = x->world;
+        for (int r = 0; r < x->world; ++r) {
+            sinks.ptr[r] = reinterpret_cast<int2*>(x->region(r, parity)) + (size_t)x->rank * x->per_rank + s;
+            sinks.flag[r] = x->flags(r) + x->rank;
+        }
+        if (s + m == n) {                      // last micro-batch: its fc8 kernel publishes the epoch
+            sinks.epoch = epoch;
+            sinks.done = x->done;
+        }
+        mark(h, 0, st);
+        if ((rc = encode_front(h, rows_dev + s * SVX_ROW_FIELDS, m, st))) return rc;
+        if ((rc = run_cnn(h, m, nullptr, nullptr, nullptr, st, h->use_front, &sinks))) return rc;
+    }
+    int rc;
+    if ((rc = launch_exchange_wait(x->flags(x->rank), x->world, epoch, x->timeout_ns, x->error, st))) return rc;
+    SVX_CUDA_CHECK(cudaEventRecord(h->busy, st));
+    if (gathered_dev) *gathered_dev = reinterpret_cast<const svx_call*>(x->region(x->rank, parity));
+    return SVX_OK;
+}
+
+int svx_exchange_status(svx_exchange* x) {
+    if (!x) return fail(SVX_ERR_INVALID, "svx_exchange_status: NULL exchange");
+    DeviceGuard guard(x->device);
+    unsigned int err = 0;
+    SVX_CUDA_CHECK(cudaDeviceSynchronize());
+    SVX_CUDA_CHECK(cudaMemcpy(&err, x->error, sizeof(err), cudaMemcpyDeviceToHost));
+    if (err != 0) {
+        SVX_CUDA_CHECK(cudaMemset(x->error, 0, sizeof(err)));
+        return fail(SVX_ERR_CUDA, "svx_classify_exchange: timed out waiting for rank " + std::to_string(err - 1));
+    }
+    return SVX_OK;
+}
+
+void svx_exchange_destroy(svx_exchange* x) {
+    if (!x) return;
+    DeviceGuard guard(x->device);
+    cudaDeviceSynchronize();
+    for (int r = 0; r < x->world; ++r)
+        if (x->opened[r]) cudaIpcCloseMemHandle(x->base[r]);
+    cudaFree(x->local);
+    cudaFree(x->done);
+    delete x;
 }
 
 int svx_debug_activation(svx_handle* h, const char* name, int64_t n, float* out_host) {

@@ -6,6 +6,8 @@ results at the end.  Contiguity preserves file order, which the region-flush log
 on GPUs, gloo in the CPU tests)."""
 from __future__ import annotations
 
+import ctypes
+
 import numpy as np
 import torch
 import torch.distributed as dist
@@ -55,3 +57,74 @@ def classify_sharded(classify_fn, rows: np.ndarray, device=None, group=None):
     p = torch.from_numpy(np.ascontiguousarray(probs, dtype=np.float32)).to(dev)
     fl, fp = gather_results(l, p, n, group)
     return fl.cpu().numpy(), fp.cpu().numpy()
+
+
+class _DeviceView:
+    """A library-owned device buffer exposed through ``__cuda_array_interface__`` (zero copy)."""
+
+    def __init__(self, ptr: int, shape, typestr: str):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr,
+                                         "data": (int(ptr), False), "version": 2}
+
+
+class Exchange:
+    """Fused result exchange (``include/svx.h``, SURVEY.md §8(e) "fused variant"): the fc8 kernel of
+    every rank stores its per-site ``(label, score)`` calls straight into the gathered buffer of
+    EVERY rank over NVLink and publishes a flag; no collective kernel runs on the path.
+
+    ``torch.distributed`` is used once, at construction, to all-gather the 64-byte CUDA IPC handles.
+    Every rank must call :meth:`classify` the same number of times, with at most ``sites_per_rank``
+    rows (use :func:`shard_rows`)."""
+
+    def __init__(self, classifier, sites_per_rank: int, group=None):
+        from . import _lib
+        self._lib = _lib.load()
+        self._check = _lib.check
+        self.clf = classifier
+        self.per = int(sites_per_rank)
+        distributed = dist.is_available() and dist.is_initialized()
+        self.world = dist.get_world_size(group) if distributed else 1
+        self.rank = dist.get_rank(group) if distributed else 0
+        x = ctypes.c_void_p()
+        self._check(self._lib.svx_exchange_create(classifier._h, self.rank, self.world, self.per,
+                                                  ctypes.byref(x)), "svx_exchange_create")
+        self._x = x
+        if self.world > 1:
+            mine = np.zeros(_lib.IPC_HANDLE_BYTES, dtype=np.uint8)
+            self._check(self._lib.svx_exchange_export(self._x, mine.ctypes.data), "svx_exchange_export")
+            on_gpu = dist.get_backend(group) == "nccl"
+            dev = classifier.torch_device if on_gpu else torch.device("cpu")
+            t = torch.from_numpy(mine).to(dev)
+            out = torch.empty((self.world * _lib.IPC_HANDLE_BYTES,), dtype=torch.uint8, device=dev)
+            dist.all_gather_into_tensor(out, t, group=group)
+            handles = np.ascontiguousarray(out.cpu().numpy())
+            self._check(self._lib.svx_exchange_attach(self._x, handles.ctypes.data), "svx_exchange_attach")
+            dist.barrier(group)                     # every rank has mapped every buffer
+
+    def classify(self, rows_dev: torch.Tensor):
+        """rows of this rank's shard (cuda int32 [n<=per,12]) -> (labels int32[world*per], scores
+        float32[world*per]) in rank-major (= file) order: zero-copy views of the gathered buffer,
+        valid after the current stream's work and until the next-but-one call."""
+        clf = self.clf
+        assert rows_dev.dtype == torch.int32 and rows_dev.is_contiguous() and rows_dev.device == clf.torch_device
+        ptr = ctypes.c_void_p()
+        self._check(self._lib.svx_classify_exchange(clf._h, self._x, rows_dev.data_ptr(), rows_dev.shape[0],
+                                                    ctypes.byref(ptr), clf._stream()), "svx_classify_exchange")
+        calls = torch.as_tensor(_DeviceView(ptr.value, (self.world * self.per, 2), "<i4"),
+                                device=clf.torch_device)
+        return calls[:, 0], calls[:, 1].view(torch.float32)
+
+    def status(self) -> None:
+        """Synchronises and raises if a rank failed to show up within the timeout."""
+        self._check(self._lib.svx_exchange_status(self._x), "svx_exchange_status")
+
+    def close(self) -> None:
+        if getattr(self, "_x", None):
+            self._lib.svx_exchange_destroy(self._x)
+            self._x = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

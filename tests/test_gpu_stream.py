@@ -1,0 +1,118 @@
+"""GPU: the BASELINE configs beyond config 2, through the same C-ABI entries.
+
+* config 3 (100 k HiFi-profile sites) and config 5 (ONT-profile sites) at full size, checked through
+  size-independent properties plus known-answer rows embedded in the stream;
+* config 4 (region-grouped stream -> VCF text): BED text -> native parser -> GPU classify ->
+  ``calls.call_chromosome`` against the same pipeline fed by the CPU oracle's labels and scores
+  (parity definition of SURVEY.md §8(c): records identical, QUAL within +-2);
+* the 8-byte-per-site entries: ``svx_classify_device_calls`` and the fused exchange
+  (``svx_classify_exchange``) at world size 1 (the 2-rank form is ``tools/exchange_check.py``,
+  run under torchrun on a multi-GPU box)."""
+import os
+import types
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import alexnet, encoder_c
+from svision_b200 import bed, calls, classifier as C, sharded, sites
+
+pytestmark = pytest.mark.gpu
+
+SOFTMAX_TOL = 1e-3          # BASELINE.json north_star
+
+
+@pytest.fixture(scope="module")
+def clf(synthetic_weights):
+    c = C.Classifier(synthetic_weights, device=0, max_batch=2048)
+    yield c
+    c.close()
+
+
+def test_calls_entry_equals_labels_and_winning_softmax(clf):
+    rows = sites.make_sites_p1(5000, seed=sites.SEED_CONFIG3)           # ragged: 2048 + 2048 + 904
+    rd = clf.rows_to_device(rows)
+    labels, probs = clf.classify_device(rd)
+    l2, s2 = clf.classify_device_calls(rd)
+    torch.cuda.synchronize()
+    assert torch.equal(labels, l2)
+    assert torch.equal(probs.gather(1, labels.long().unsqueeze(1)).squeeze(1), s2)
+
+
+def test_fused_exchange_world_size_one(clf):
+    """Same kernels, sinks and flag protocol as the multi-GPU form (the only sink is local)."""
+    per = 3000
+    x = sharded.Exchange(clf, per)
+    try:
+        for n, seed in ((3000, 1), (1234, 2), (1, 3), (2999, 4)):        # both parities, ragged sizes
+            rows = sites.make_sites_p1(n, seed=seed)
+            rd = clf.rows_to_device(rows)
+            labels, scores = x.classify(rd)
+            got_l, got_s = labels[:n].clone(), scores[:n].clone()
+            ref_l, ref_s = clf.classify_device_calls(rd)
+            torch.cuda.synchronize()
+            x.status()
+            assert torch.equal(got_l, ref_l) and torch.equal(got_s, ref_s), n
+        with pytest.raises(Exception):
+            x.classify(clf.rows_to_device(sites.make_sites_p1(per + 1, seed=5)))
+    finally:
+        x.close()
+
+
+@pytest.mark.parametrize("profile,seed", [("hifi", sites.SEED_CONFIG3), ("ont", sites.SEED_CONFIG5)])
+def test_config3_config5_full_size(clf, cnn_golden, profile, seed):
+    """100 000 sites: permutation equivariance (bit-exact), shard independence, softmax rows sum to
+    one, and 256 known-answer rows hidden in the stream come back with the golden results."""
+    n = 100_000
+    rows = sites.make_sites_p1(n, seed=seed, profile=profile)
+    rng = np.random.default_rng(seed)
+    where = np.sort(rng.choice(n, size=256, replace=False))
+    rows[where] = cnn_golden["rows"][:256]
+    labels, probs = clf.classify(rows)
+    assert np.abs(probs.sum(1) - 1).max() < 1e-5
+    assert np.array_equal(labels, probs.argmax(1).astype(np.int32))
+    # known answers (fp64 referee of the oracle, tests/golden/cnn_golden.npz)
+    ref_logits = torch.from_numpy(cnn_golden["logits_fp64"][:256])
+    assert np.array_equal(labels[where], ref_logits.argmax(1).numpy().astype(np.int32))
+    assert np.abs(probs[where] - torch.softmax(ref_logits, 1).numpy()).max() < SOFTMAX_TOL
+    # sites are independent: any permutation permutes the results bit for bit
+    perm = rng.permutation(n)
+    l2, p2 = clf.classify(rows[perm])
+    assert np.array_equal(labels[perm], l2) and np.array_equal(probs[perm], p2)
+    # contiguous shards as ranks would take them
+    for r in range(3):
+        a, b, _ = sharded.shard_bounds(n, 3, r)
+        ls, ps = clf.classify(rows[a:b])
+        assert np.array_equal(ls, labels[a:b]) and np.array_equal(ps, probs[a:b])
+
+
+def _options(min_support):
+    return types.SimpleNamespace(min_support=min_support, qname=True, min_sv_size=50, min_mapq=10,
+                                 min_gt_depth=4, homo_thresh=0.8, hete_thresh=0.2, bam_path="synthetic.bam")
+
+
+def test_config4_stream_to_vcf_matches_oracle_pipeline(clf, synthetic_weights, tmp_path):
+    n = 1536
+    table = sites.make_region_table(n, seed=sites.SEED_CONFIG4)
+    path = tmp_path / "chr1.segments.all.bed"
+    path.write_text("\n".join(sites.table_to_bed_lines(table)) + "\n")
+    parsed = bed.read_segments_bed(str(path))
+    assert np.array_equal(parsed.rows, table.rows)
+    aln = sites.make_alignments(table, seed=2)
+    at = calls.AlignmentTable(aln["contig_length"], aln["reference_start"], aln["reference_end"],
+                              aln["mapping_quality"], aln["is_unmapped"], aln["is_secondary"], aln["query_name"])
+    labels, probs = clf.classify(parsed.rows)
+    torch.set_num_threads(os.cpu_count() or 1)
+    ref_l, ref_p, _ = alexnet.classify(encoder_c.encode_f32(parsed.rows), synthetic_weights, torch.float32, batch=128)
+    assert np.array_equal(labels, ref_l.astype(np.int32))
+    assert np.abs(probs - ref_p).max() < SOFTMAX_TOL
+    for min_support in (1, 3):
+        opt = _options(min_support)
+        got = calls.call_chromosome(parsed, labels, probs, opt, at)
+        ref = calls.call_chromosome(parsed, ref_l.astype(np.int32), ref_p.astype(np.float32), opt, at)
+        assert len(got) == len(ref) and (min_support > 1 or len(got) > 0)
+        for (q1, line1), (q2, line2) in zip(got, ref):
+            f1, f2 = line1.split("\t"), line2.split("\t")
+            assert abs(float(q1) - float(q2)) <= 2 and abs(float(f1[5]) - float(f2[5])) <= 2
+            assert f1[:5] == f2[:5] and f1[6:] == f2[6:]          # POS/ID/ALT, INFO, GT:DR:DV identical

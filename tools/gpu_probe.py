@@ -159,7 +159,7 @@ def stage_counters():
     w = weights.synthetic_weights()
     n = 2048
     os.environ["SVX_DBG"] = "1"
-    for prec in ("3pass", "1pass"):
+    for prec in os.environ.get("PROBE_PREC", "3pass,1pass").split(","):
         clf = C.Classifier(w, device=0, max_batch=2048, precision=prec)
         rd = clf.rows_to_device(sites.make_sites_p1(n, seed=sites.SEED_CONFIG2))
         for _ in range(2):

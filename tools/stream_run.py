@@ -1,0 +1,84 @@
+"""BASELINE config 4 / 5 as a whole-stream run on one GPU:
+
+    python tools/stream_run.py [--rows 500000] [--profile hifi|ont] [--out DIR]
+
+synthetic region-grouped stream -> 23-column BED text -> native parser (svx_bed_parse) -> encode +
+classify on the GPU through the host entry (svx_classify) -> region aggregation, VCF records and
+one-pass genotyping (svision_b200.calls) -> <out>/chr1.predict.s3.{vcf,score.txt}.  Prints one JSON
+line with the rows/s of every stage.  Weights are synthetic (no checkpoint exists here), so the calls
+are not biology; the run exercises formats and stage throughputs at whole-genome row counts."""
+import argparse
+import json
+import os
+import sys
+import tempfile
+import time
+import types
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from svision_b200 import bed, calls, classifier as C, sites, weights  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--rows", type=int, default=500_000)
+    ap.add_argument("--profile", default="hifi", choices=["hifi", "ont"])
+    ap.add_argument("--out", default=None)
+    a = ap.parse_args()
+    out_dir = a.out or tempfile.mkdtemp(prefix="svx_stream_")
+    os.makedirs(out_dir, exist_ok=True)
+    seed = sites.SEED_CONFIG4 if a.profile == "hifi" else sites.SEED_CONFIG5
+    res = {"rows": a.rows, "profile": a.profile}
+
+    t = time.perf_counter()
+    table = sites.make_region_table(a.rows, seed=seed, profile=a.profile)
+    aln = sites.make_alignments(table, seed=2)
+    bed_path = os.path.join(out_dir, "chr1.segments.all.bed")
+    with open(bed_path, "w") as f:
+        f.write("\n".join(sites.table_to_bed_lines(table)) + "\n")
+    res["generate_s"] = round(time.perf_counter() - t, 2)
+    res["regions"] = len(set(table.region.tolist()))
+    res["bed_mb"] = round(os.path.getsize(bed_path) / 1e6, 1)
+
+    t = time.perf_counter()
+    parsed = bed.read_segments_bed(bed_path)
+    dt = time.perf_counter() - t
+    res["bed_parse_rows_per_s"] = round(a.rows / dt)
+    assert np.array_equal(parsed.rows, table.rows)
+
+    clf = C.Classifier(weights.synthetic_weights(), device=0, max_batch=2048)
+    clf.classify(parsed.rows[:4096])                                     # warm-up
+    t = time.perf_counter()
+    labels, probs = clf.classify(parsed.rows)
+    dt = time.perf_counter() - t
+    res["classify_sites_per_s"] = round(a.rows / dt)
+    res["classify_s"] = round(dt, 3)
+    res["label_histogram"] = np.bincount(labels, minlength=5).tolist()
+
+    opt = types.SimpleNamespace(min_support=3, qname=False, min_sv_size=50, min_mapq=10, min_gt_depth=4,
+                                homo_thresh=0.8, hete_thresh=0.2, bam_path="synthetic.bam")
+    t = time.perf_counter()
+    at = calls.AlignmentTable(aln["contig_length"], aln["reference_start"], aln["reference_end"],
+                              aln["mapping_quality"], aln["is_unmapped"], aln["is_secondary"], aln["query_name"])
+    res["alignment_index_s"] = round(time.perf_counter() - t, 3)
+    t = time.perf_counter()
+    records = calls.call_chromosome(parsed, labels, probs, opt, at)
+    dt = time.perf_counter() - t
+    res["calls_rows_per_s"] = round(a.rows / dt)
+    res["calls_s"] = round(dt, 3)
+    t = time.perf_counter()
+    calls.write_chromosome(os.path.join(out_dir, "chr1.predict.s3"), records)
+    res["write_s"] = round(time.perf_counter() - t, 3)
+    res["records"] = len(records)
+    total = a.rows / res["bed_parse_rows_per_s"] + res["classify_s"] + res["alignment_index_s"] + res["calls_s"] + res["write_s"]
+    res["pipeline_rows_per_s"] = round(a.rows / total)
+    clf.close()
+    print(json.dumps(res), flush=True)
+
+
+if __name__ == "__main__":
+    main()
