@@ -85,21 +85,45 @@ class Exchange:
         distributed = dist.is_available() and dist.is_initialized()
         self.world = dist.get_world_size(group) if distributed else 1
         self.rank = dist.get_rank(group) if distributed else 0
+        self._x = None
+        err = None
         x = ctypes.c_void_p()
-        self._check(self._lib.svx_exchange_create(classifier._h, self.rank, self.world, self.per,
-                                                  ctypes.byref(x)), "svx_exchange_create")
-        self._x = x
-        if self.world > 1:
-            mine = np.zeros(_lib.IPC_HANDLE_BYTES, dtype=np.uint8)
-            self._check(self._lib.svx_exchange_export(self._x, mine.ctypes.data), "svx_exchange_export")
-            on_gpu = dist.get_backend(group) == "nccl"
-            dev = classifier.torch_device if on_gpu else torch.device("cpu")
-            t = torch.from_numpy(mine).to(dev)
-            out = torch.empty((self.world * _lib.IPC_HANDLE_BYTES,), dtype=torch.uint8, device=dev)
-            dist.all_gather_into_tensor(out, t, group=group)
-            handles = np.ascontiguousarray(out.cpu().numpy())
-            self._check(self._lib.svx_exchange_attach(self._x, handles.ctypes.data), "svx_exchange_attach")
-            dist.barrier(group)                     # every rank has mapped every buffer
+        mine = np.zeros(_lib.IPC_HANDLE_BYTES + 1, dtype=np.uint8)      # handle + "this rank is fine"
+        try:
+            self._check(self._lib.svx_exchange_create(classifier._h, self.rank, self.world, self.per,
+                                                      ctypes.byref(x)), "svx_exchange_create")
+            self._x = x
+            if self.world > 1:
+                self._check(self._lib.svx_exchange_export(self._x, mine.ctypes.data), "svx_exchange_export")
+            mine[-1] = 1
+        except Exception as e:                      # noqa: BLE001 -- agreed on collectively below
+            err = e
+        if self.world == 1:
+            if err is not None:
+                raise err
+            return
+        # every collective below is executed by every rank, whatever happened locally, so that a
+        # failure on one rank raises on all of them instead of leaving the others waiting
+        on_gpu = dist.get_backend(group) == "nccl"
+        dev = classifier.torch_device if on_gpu else torch.device("cpu")
+        out = torch.empty((self.world * mine.size,), dtype=torch.uint8, device=dev)
+        dist.all_gather_into_tensor(out, torch.from_numpy(mine).to(dev), group=group)
+        table = out.cpu().numpy().reshape(self.world, mine.size)
+        if err is None and not table[:, -1].all():
+            err = RuntimeError(f"exchange setup failed on rank(s) {np.flatnonzero(table[:, -1] == 0).tolist()}")
+        ok = 0
+        if err is None:
+            try:
+                handles = np.ascontiguousarray(table[:, :-1])
+                self._check(self._lib.svx_exchange_attach(self._x, handles.ctypes.data), "svx_exchange_attach")
+                ok = 1
+            except Exception as e:                  # noqa: BLE001
+                err = e
+        flag = torch.tensor([ok], dtype=torch.int32, device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)        # also: every rank has mapped every buffer
+        if int(flag.item()) == 0:
+            self.close()
+            raise err if err is not None else RuntimeError("exchange attach failed on another rank")
 
     def classify(self, rows_dev: torch.Tensor):
         """rows of this rank's shard (cuda int32 [n<=per,12]) -> (labels int32[world*per], scores

@@ -179,6 +179,38 @@ def test_sharded_all_gather_gloo_world2(n):
     assert res == [(0, True, True), (1, True, True)]
 
 
+def _exchange_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+
+    class NoGpuClassifier:                      # the C-ABI rejects a NULL handle: setup fails locally
+        _h = None
+        torch_device = torch.device("cpu")
+
+    try:
+        sharded.Exchange(NoGpuClassifier(), 100)
+        q.put((rank, "no error"))
+    except Exception as e:                      # noqa: BLE001
+        q.put((rank, type(e).__name__))
+    dist.destroy_process_group()
+
+
+def test_exchange_setup_failure_raises_on_every_rank_gloo_world2():
+    """A rank whose exchange setup fails must not leave the others waiting in a collective: the
+    failure is agreed on and raised everywhere (here both ranks fail: no GPU, no handle)."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 500) + 777
+    procs = [ctx.Process(target=_exchange_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+    assert [r for r, _ in res] == [0, 1] and all(name != "no error" for _, name in res)
+
+
 def test_bed_reader_on_real_reference_output():
     """The BED written by the reference's writer_cluster_to_file for its demo BAM."""
     here = os.path.dirname(__file__)
