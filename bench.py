@@ -44,8 +44,8 @@ CNN_FLOP_PER_SITE = 1_440_662_592            # SURVEY.md §8(a) layer table (2 x
 FC8_FLOP_PER_SITE = 2 * 20_480               # runs on CUDA cores, not in the tensor-core kernel
 ENC_BYTES_PER_SITE = 48 + 227 * 227 * 3 * 2  # 16-bit image is what is emitted
 # dram__bytes_read.sum + dram__bytes_write.sum of the conv2 launch (2048 sites) from the committed
-# `ncu --set full` capture profiles/r1d_ncu_full_summary.txt: 662.8 MB + 1711 MB
-CONV2_DRAM_BYTES_PER_SITE = (662.823e6 + 1.711e9) / 2048
+# `ncu --set full` capture profiles/r1l_ncu_full_summary.txt: 662.9 MB read + 1478.4 MB written
+CONV2_DRAM_BYTES_PER_SITE = (662.876e6 + 1478.410e6) / 2048
 #: algorithmic FLOPs per site of each tensor-core layer (groups honoured, no padding credit)
 LAYER_FLOP = {"conv1": 2 * 105_415_200, "conv2": 2 * 223_948_800, "conv3": 2 * 149_520_384,
               "conv4": 2 * 112_140_288, "conv5": 2 * 74_760_192, "fc6": 2 * 37_748_736,
@@ -379,9 +379,10 @@ def run_gpu(args):
                          "frac": layers["conv2"].get("tflops_algorithmic", 0.0) / peak if peak else None,
                          "traffic": CONV2_DRAM_BYTES_PER_SITE * sites_rank / max(prof["conv2"][1], 1),
                          "traffic_note": "bytes per launch, from ncu dram__bytes_read.sum + "
-                                         "dram__bytes_write.sum (profiles/r1d_ncu_full_summary.txt) scaled to "
+                                         "dram__bytes_write.sum (profiles/r1l_ncu_full_summary.txt) scaled to "
                                          "this run's sites per launch; algorithmic bytes are the same "
-                                         "(x2 operand read once, y2 written once)",
+                                         "(x2 operand read once = 0.66 GB, the 27x27 valid rows of y2 "
+                                         "written once = 1.53 GB per 2048 sites)",
                          "ms_per_launch": layers["conv2"]["ms_per_launch"],
                          "share_of_step": prof["conv2"][0] / ms_total if ms_total > 0 else None,
                          "peak_source": peaks["source"] + ", bf16 sustained",
