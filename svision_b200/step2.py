@@ -1,0 +1,180 @@
+"""Step 2 of the SVision driver ("CNN prediction", ``SVision:296-341``) around the B200 path:
+
+    predict_chromosomes   <- predict_one_chrom + the multiprocessing pool      (SVision:298-323)
+    score_range           <- cal_scores_max_min + np.max / np.min               (output.py:601-612, SVision:331-334)
+    merge_chromosomes     <- merge_split_vcfs                                   (output.py:251-348)
+    run_step2             <- the three in sequence                              (SVision:296-341)
+
+What changes and why (SURVEY.md H6, §8(b) "Threading / processes"): the reference forks one worker
+per chromosome, each building a TF session and restoring the checkpoint again, and never reads the
+workers' error strings.  A CUDA context must not be forked and the model should be loaded once, so
+the chromosomes run in one in-process loop over ONE classifier handle, and errors propagate.  What
+does not change: the per-chromosome files ``<chrom>.predict.s<k>.{vcf,score.txt}`` and the merged
+``<sample>.svision.s<k>.vcf`` are byte-identical to what the reference's functions write for the same
+labels and scores (``tests/test_step2.py`` runs the reference's own ``merge_split_vcfs`` beside this).
+
+The contig lines of the header come from the genome's ``.fai`` (name, length per line), which is what
+``pysam.FastaFile`` serves at ``output.py:264-268``; no htslib is needed for that.
+"""
+from __future__ import annotations
+
+import logging
+import os
+from typing import Callable, Iterable, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import predict as _predict
+
+SVISION_VERSION = "1.4"                         # src/version.py (printed into the header: output.py:262)
+
+# The fixed part of the header (output.py:270-299): (key, attributes) in file order.
+_HEADER_FIELDS = (
+    ("CHROM", 'CHROM=XXX,Description="Chromosome ID"'),
+    ("POS", 'POS=XXX,Description="Start position of the SV described in this region"'),
+    ("ID", 'ID=XXX,Description="ID of the SV described in this region"'),
+    ("REF", 'REF=N,Description="Ref\'s sequence in that region, default=N"'),
+    ("QUAL", 'QUAL=XXX,Description="The SV quality of the SV described in this region"'),
+    ("ALT", 'ID=SV,Description="Simple SVs"'),
+    ("ALT", 'ID=CSV,Description="Complex or nested SVs"'),
+    ("FILTER", 'ID=Covered,Description="Covered mean the SV is spanned by reads"'),
+    ("FILTER", 'ID=Uncovered,Description="UnCovered mean the SV is not spanned by reads"'),
+    ("FILTER", 'ID=Clustered,Description="Clustered mean the SV is not spanned by reads, but can be cluster '
+               'together with others"'),
+    ("INFO", 'ID=END,Number=1,Type=Integer,Description="End position of the SV described in this region"'),
+    ("INFO", 'ID=SVLEN,Number=1,Type=Integer,Description="Difference in length between REF and ALT alleles"'),
+    ("INFO", 'ID=BKPS,Number=.,Type=String,Description="All breakpoints (length-start-end) in this region, '
+             'where CSV might contain multiple breakpoints."'),
+    ("INFO", 'ID=SVTYPE,Number=1,Type=String,Description="CNN predicted SV type, containing INS, DEL, DUP, tDUP '
+             '(tandem duplication) and INV"'),
+    ("INFO", 'ID=SUPPORT,Number=1,Type=Integer,Description="SV support number in this region"'),
+    ("INFO", 'ID=READS,Number=.,Type=String,Description="SV support read names in this region"'),
+)
+_HEADER_GRAPH = (                                # only with --graph (output.py:288-292)
+    ("INFO", 'ID=GraphID,Number=1,Type=String,Description="The corresponding graph id of isomorphic CSV graph '
+             'structures"'),
+    ("INFO", 'ID=GFA_FILE_PREFIX,Number=1,Type=String,Description="File name of CSV corresponding GFA file"'),
+    ("INFO", 'ID=GFA_S,Number=1,Type=String,Description="Nodes contained in a CSV graph represented based on GFA '
+             'format"'),
+    ("INFO", 'ID=GFA_L,Number=1,Type=String,Description="Links contained in a CSV graph represented based on GFA '
+             'format"'),
+)
+_HEADER_FORMAT = (
+    ("FORMAT", 'ID=GT,Number=1,Type=String,Description="Genotype"'),
+    ("FORMAT", 'ID=DR,Number=1,Type=Integer,Description="high-quality reference reads"'),
+    ("FORMAT", 'ID=DV,Number=1,Type=Integer,Description="high-quality variant reads"'),
+)
+
+
+def contigs_from_fai(genome_path: str) -> List[Tuple[str, int]]:
+    """``[(name, length), ...]`` in index order from ``<genome>.fai`` (what ``pysam.FastaFile(genome)
+    .references`` / ``.get_reference_length`` return: output.py:264-268)."""
+    out = []
+    with open(genome_path + ".fai") as f:
+        for line in f:
+            cols = line.rstrip("\n").split("\t")
+            if len(cols) >= 2 and cols[0]:
+                out.append((cols[0], int(cols[1])))
+    return out
+
+
+def header_lines(contigs: Iterable[Tuple[str, int]], sample: str, graph: bool = False) -> List[str]:
+    lines = ["##fileformat=VCFv4.3", f"##source=SVision v{SVISION_VERSION}"]
+    lines += [f"##contig=<ID={name},length={length}>" for name, length in contigs]
+    fields = _HEADER_FIELDS + (_HEADER_GRAPH if graph else ()) + _HEADER_FORMAT
+    lines += [f"##{key}=<{attrs}>" for key, attrs in fields]
+    lines.append("#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT\t" + str(sample))
+    return lines
+
+
+def predict_paths(predict_dir: str, chrom: str, min_support) -> str:
+    """Prefix of a chromosome's result files (SVision:301)."""
+    return os.path.join(predict_dir, f"{chrom}.predict.s{min_support}")
+
+
+def predict_chromosomes(chroms: Sequence[str], segments_dir: str, predict_dir: str, options,
+                        classifier=None, genotype_for: Optional[Callable] = None) -> dict:
+    """Runs ``Predict.run`` for every chromosome in order, in this process, on one classifier
+    (``SVision:298-323`` used a fork pool of ``thread_num // 3`` workers).  ``genotype_for(chrom)``
+    returns what :func:`svision_b200.predict.run_predict` accepts as ``genotype`` (default: the BAM of
+    ``options.bam_path`` is read once per chromosome).  A chromosome without a segments file is
+    skipped, as the reference's worker fails on it silently.  Returns ``{chrom: n_records}``."""
+    os.makedirs(predict_dir, exist_ok=True)
+    clf = classifier if classifier is not None else _predict.get_classifier(options.model_path)
+    done = {}
+    for chrom in chroms:
+        bed_path = os.path.join(segments_dir, chrom + ".segments.all.bed")
+        if not os.path.exists(bed_path):
+            logging.warning("no segments file for %s (%s): skipped", chrom, bed_path)
+            continue
+        genotype = genotype_for(chrom) if genotype_for is not None else None
+        done[chrom] = _predict.run_predict(bed_path, predict_paths(predict_dir, chrom, options.min_support),
+                                           options, classifier=clf, chrom=chrom, genotype=genotype)
+    return done
+
+
+def score_range(predict_dir: str) -> Tuple[np.float64, np.float64]:
+    """(max, min) over every ``*score.txt`` line that is not ``0`` (output.py:601-612, SVision:331-334).
+    The reference prints 'Empty output in the score file' and exits when there is none; here that is a
+    ``ValueError`` for the caller to report."""
+    scores = []
+    for name in os.listdir(predict_dir):
+        if "score.txt" not in name:
+            continue
+        with open(os.path.join(predict_dir, name)) as f:
+            for line in f:
+                t = line.strip()
+                if t == "0":
+                    continue
+                scores.append(float(t))
+    if not scores:
+        raise ValueError("no scores under " + predict_dir + ": nothing was called")
+    return np.max(scores), np.min(scores)
+
+
+def merge_chromosomes(predict_dir: str, merged_vcf_path: str, max_score, min_score, chroms: Sequence[str],
+                      options, contigs: Optional[Iterable[Tuple[str, int]]] = None) -> int:
+    """Header + every chromosome's records with final IDs and rescaled QUAL (output.py:251-348).
+
+    IDs count records whose (POS, END) differ from the previous record's, from 0; a record repeating
+    the previous (POS, END) becomes ``<id>_<k>`` (output.py:318-331).  QUAL becomes
+    ``int(100 - round((q - min) / (max - min), 2) * 100)``, or 100 when all scores are equal
+    (output.py:334-341).  Returns the number of records written."""
+    if contigs is None:
+        contigs = contigs_from_fai(options.genome)
+    span = max_score - min_score
+    n = 0
+    with open(merged_vcf_path, "w") as out:
+        out.write("\n".join(header_lines(contigs, options.sample, bool(getattr(options, "graph", False)))) + "\n")
+        serial = -1
+        for chrom in chroms:
+            prev_key, sub = None, 1
+            with open(predict_paths(predict_dir, chrom, options.min_support) + ".vcf") as f:
+                for record in f:
+                    cols = record.split("\t")
+                    key = (cols[1], cols[7].split(";")[0][4:])              # POS, END=<..>
+                    if key == prev_key:
+                        cols[2] = f"{serial}_{sub}"
+                        sub += 1
+                    else:
+                        prev_key, sub = key, 1
+                        serial += 1
+                        cols[2] = str(serial)
+                    q = 100
+                    if max_score != min_score:
+                        q = int(100 - (round((float(cols[5]) - min_score) / span, 2) * 100))
+                    cols[5] = str(q)
+                    out.write("\t".join(cols))
+                    n += 1
+    return n
+
+
+def run_step2(chroms: Sequence[str], segments_dir: str, predict_dir: str, options, classifier=None,
+              genotype_for: Optional[Callable] = None, contigs=None) -> str:
+    """``SVision:296-341``: predict every chromosome, then score range and merge.  Returns the path of
+    ``<out_path>/<sample>.svision.s<min_support>.vcf``."""
+    done = predict_chromosomes(chroms, segments_dir, predict_dir, options, classifier, genotype_for)
+    hi, lo = score_range(predict_dir)
+    merged = os.path.join(options.out_path, f"{options.sample}.svision.s{options.min_support}.vcf")
+    merge_chromosomes(predict_dir, merged, hi, lo, [c for c in chroms if c in done], options, contigs)
+    return merged

@@ -20,7 +20,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
-from svision_b200 import bed, calls, classifier as C, sites, weights  # noqa: E402
+from svision_b200 import bed, calls, classifier as C, sites, step2, weights  # noqa: E402
 
 
 def main():
@@ -28,6 +28,9 @@ def main():
     ap.add_argument("--rows", type=int, default=500_000)
     ap.add_argument("--profile", default="hifi", choices=["hifi", "ont"])
     ap.add_argument("--out", default=None)
+    ap.add_argument("--chroms", type=int, default=0,
+                    help="also run the whole Step 2 (svision_b200.step2: predict every chromosome on one "
+                         "classifier, score range, merged VCF) over this many extra chromosomes of rows/10 rows")
     a = ap.parse_args()
     out_dir = a.out or tempfile.mkdtemp(prefix="svx_stream_")
     os.makedirs(out_dir, exist_ok=True)
@@ -76,6 +79,27 @@ def main():
     res["records"] = len(records)
     total = a.rows / res["bed_parse_rows_per_s"] + res["classify_s"] + res["alignment_index_s"] + res["calls_s"] + res["write_s"]
     res["pipeline_rows_per_s"] = round(a.rows / total)
+    if a.chroms > 0:
+        seg_dir, pred_dir = os.path.join(out_dir, "segments"), os.path.join(out_dir, "predict_results")
+        os.makedirs(seg_dir, exist_ok=True)
+        names, aligns, n_rows = [f"chr{k + 1}" for k in range(a.chroms)], {}, 0
+        for k, chrom in enumerate(names):
+            t_k = sites.make_region_table(max(a.rows // 10, 1000), seed=seed + 100 + k, profile=a.profile, contig=chrom)
+            al = sites.make_alignments(t_k, seed=7 + k)
+            aligns[chrom] = calls.AlignmentTable(al["contig_length"], al["reference_start"], al["reference_end"],
+                                                 al["mapping_quality"], al["is_unmapped"], al["is_secondary"],
+                                                 al["query_name"])
+            with open(os.path.join(seg_dir, chrom + ".segments.all.bed"), "w") as f:
+                f.write("\n".join(sites.table_to_bed_lines(t_k)) + "\n")
+            n_rows += len(t_k)
+        opt.sample, opt.out_path, opt.graph, opt.model_path = "synthetic", out_dir, False, "unused"
+        t = time.perf_counter()
+        merged = step2.run_step2(names, seg_dir, pred_dir, opt, classifier=clf, genotype_for=aligns.get,
+                                 contigs=[(c, 250_000_000) for c in names])
+        dt = time.perf_counter() - t
+        res["step2"] = {"chromosomes": a.chroms, "rows": n_rows, "rows_per_s": round(n_rows / dt),
+                        "merged_records": sum(1 for l in open(merged) if not l.startswith("#")),
+                        "merged_vcf": os.path.basename(merged)}
     clf.close()
     print(json.dumps(res), flush=True)
 
