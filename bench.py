@@ -39,7 +39,10 @@ sys.path.insert(0, ROOT)
 METRIC = "candidate SV sites/sec (encode+CNN)"
 UNIT = "sites/s"
 SITES_PER_GPU = 10_000
-MICRO_BATCH = int(os.environ.get("SVX_BENCH_MICRO_BATCH", 2048))
+# sites resident on the device at once.  One micro-batch per step: measured 306 k sites/s against 300 k
+# with 2048-site micro-batches (fc6/fc7 get 640 tiles for 74 CTA pairs = 96 % full waves instead of
+# 128 tiles = 86 %, and the front end / pools / fc8 lose their per-launch tails); needs ~40 GB of HBM
+MICRO_BATCH = int(os.environ.get("SVX_BENCH_MICRO_BATCH", 10_000))
 CNN_FLOP_PER_SITE = 1_440_662_592            # SURVEY.md §8(a) layer table (2 x 720 331 296 MACs)
 FC8_FLOP_PER_SITE = 2 * 20_480               # runs on CUDA cores, not in the tensor-core kernel
 ENC_BYTES_PER_SITE = 48 + 227 * 227 * 3 * 2  # 16-bit image is what is emitted
@@ -364,8 +367,8 @@ def run_gpu(args):
                        "collective": {"none": "none", "nccl": "one NCCL all_gather of svx_call (label, score), 8 B/site",
                                       "fused": "fused: fc8 kernel stores svx_call (8 B/site) into every rank's "
                                                "buffer over NVLink + flag barrier (svx_classify_exchange)"}[exchange_mode] + exchange_note,
-                       "l2": "activation working set per micro-batch ~4.6 GB and fp16 hi/lo weights "
-                             "226 MB both exceed the 126 MB L2; no flush needed"},
+                       "l2": f"activation working set per micro-batch ~{2.3e-3 * min(MICRO_BATCH, n):.1f} GB and "
+                             "fp16 hi/lo weights 226 MB both exceed the 126 MB L2; no flush needed"},
             "e2e": {"value": total_sites / e2e_s, "unit": UNIT,
                     "h2d_bytes_per_step": int(n * world * 48),
                     "d2h_bytes_per_step": int(n * world * 24)},

@@ -29,7 +29,7 @@ from . import bed as _bed
 _CLASSIFIER_CACHE = {}
 
 
-def get_classifier(model_path, device: int = 0, max_batch: int = 2048):
+def get_classifier(model_path, device: int = 0, max_batch: int = 8192):
     """Process-wide classifier for ``-m model_path`` (amortises the checkpoint load)."""
     from .classifier import Classifier
     key = (str(model_path), int(device))

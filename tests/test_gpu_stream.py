@@ -116,3 +116,41 @@ def test_config4_stream_to_vcf_matches_oracle_pipeline(clf, synthetic_weights, t
             f1, f2 = line1.split("\t"), line2.split("\t")
             assert abs(float(q1) - float(q2)) <= 2 and abs(float(f1[5]) - float(f2[5])) <= 2
             assert f1[:5] == f2[:5] and f1[6:] == f2[6:]          # POS/ID/ALT, INFO, GT:DR:DV identical
+
+
+def test_config1_demo_bed_through_step2_on_the_gpu(clf, synthetic_weights, tmp_path):
+    """BASELINE config 1's rows (the reference's collection stage on its demo BAM, committed as
+    tests/golden/demo_chr9.segments.bed) through the whole Step 2 on the GPU classifier: per-chromosome
+    files + merged VCF, equal to the same run fed by the CPU oracle (QUAL within +-2 before rescaling)."""
+    import shutil
+    from svision_b200 import step2
+    seg = tmp_path / "segments"
+    seg.mkdir()
+    shutil.copy(os.path.join(os.path.dirname(__file__), "golden", "demo_chr9.segments.bed"),
+                seg / "chr9.segments.all.bed")
+
+    class OracleClassifier:
+        def classify(self, rows):
+            l, p, _ = alexnet.classify(encoder_c.encode_f32(rows), synthetic_weights, torch.float32, batch=64)
+            return l.astype(np.int32), p.astype(np.float32)
+
+    def run(classifier, name):
+        opt = types.SimpleNamespace(min_support=1, qname=False, min_sv_size=50, min_mapq=10, min_gt_depth=4,
+                                    homo_thresh=0.8, hete_thresh=0.2, bam_path="unused", graph=False,
+                                    model_path="unused", sample="demo", out_path=str(tmp_path / name))
+        os.makedirs(opt.out_path)
+        merged = step2.run_step2(["chr9"], str(seg), str(tmp_path / name / "predict_results"), opt,
+                                 classifier=classifier, genotype_for=lambda chrom: (lambda *a: ("./.", 0, 0)),
+                                 contigs=[("chr9", 138394717)])
+        per_chrom = open(tmp_path / name / "predict_results" / "chr9.predict.s1.vcf").read().splitlines()
+        return open(merged).read().splitlines(), per_chrom
+
+    torch.set_num_threads(os.cpu_count() or 1)
+    got, got_chr = run(clf, "gpu")
+    ref, ref_chr = run(OracleClassifier(), "oracle")
+    assert len(got_chr) == len(ref_chr) >= 5
+    for a, b in zip(got_chr, ref_chr):
+        fa, fb = a.split("\t"), b.split("\t")
+        assert fa[:5] == fb[:5] and fa[6:] == fb[6:] and abs(float(fa[5]) - float(fb[5])) <= 2
+    assert [l for l in got if l.startswith("#")] == [l for l in ref if l.startswith("#")]
+    assert len(got) == len(ref)
