@@ -31,6 +31,8 @@
 
 #include <math_constants.h>
 
+#include <cstdlib>
+
 namespace svx {
 
 namespace {
@@ -204,19 +206,29 @@ front_kernel(const int32_t* __restrict__ rows, long long n, const FrontParams P)
         }
         __syncthreads();
 
-        // ---- background positions: 12 channel octets x 2 planes per position, 16-byte stores
+        // ---- background positions, 16-byte stores.  Four (plane, channel group) streams of 64
+        //      threads; within a stream 6 threads (octets of 8 channels) cover one position and 10
+        //      positions go out per pass, so a thread's value, plane and column never change and
+        //      the loop body is a bit test, one multiply-add and the store (the first version
+        //      derived plane / position / octet from a flat index: 27 % of the kernel's instructions)
         __half* const planes[2] = {P.x2_hi, P.x2_lo};
         const long long img_row0 = img * G2POS;
-        for (int v = tid; v < NPOS * 24; v += FRONT_THREADS) {
-            const int plane = v >= NPOS * 12;
-            const int rem = v - plane * NPOS * 12;
-            const int p = rem / 12, o = rem - p * 12;
-            if ((dirty_mask[p >> 5] >> (p & 31)) & 1u) continue;
-            const int py = p / POOLED, px = p - py * POOLED;
-            const uint4 val = *reinterpret_cast<const uint4*>(&bg[plane][8 * o]);
-            const long long off =
-                (long long)(o / 6) * P.group_elems + (img_row0 + py * G2W + px) * P.ld + (o % 6) * 8;
-            *reinterpret_cast<uint4*>(planes[plane] + off) = val;
+        {
+            static_assert(FRONT_THREADS == 256, "four streams of 64 threads");
+            const int stream = tid >> 6, t64 = tid & 63;
+            if (t64 < 60) {
+                const int plane = stream >> 1, g = stream & 1;
+                const int pl = t64 / 6, q = t64 - 6 * pl;
+                const uint4 val = *reinterpret_cast<const uint4*>(&bg[plane][48 * g + 8 * q]);
+                __half* const dst = planes[plane] + (long long)g * P.group_elems + img_row0 * P.ld + 8 * q;
+                int py = 0, px = pl;
+                for (int p = pl; p < NPOS; p += 10) {
+                    if (!((dirty_mask[p >> 5] >> (p & 31)) & 1u))
+                        *reinterpret_cast<uint4*>(dst + (long long)((py * G2W + px) * P.ld)) = val;
+                    px += 10;
+                    if (px >= POOLED) { px -= POOLED; ++py; }
+                }
+            }
         }
 
         // ---- phase A: every dirty conv1 position once; a quarter-warp (8 lanes x 12 channels,
@@ -264,25 +276,52 @@ front_kernel(const int32_t* __restrict__ rows, long long n, const FrontParams P)
             const int p = dirty_list[i];
             const int py = p / POOLED, px = p - py * POOLED;
             float m[3] = {0.f, 0.f, 0.f}, o[3];              // ReLU folded into the max with 0
-            bool all_dirty = true;
+            // all nine slots first; if none overflowed the scratch (never, with two segments), nine
+            // independent predicated loads: one L2 round trip per position instead of one per dirty
+            // conv position
+            unsigned short sl[9];
+            bool overflow = false;
 #pragma unroll
-            for (int a = 0; a < 3; ++a)
+            for (int k = 0; k < 9; ++k) {
+                sl[k] = cslot[(2 * py + k / 3) * CONV_W + 2 * px + (k % 3)];
+                overflow |= sl[k] != CLEAN && sl[k] >= SCRATCH_SLOTS;
+            }
+            if ((P.flags & 1) && !overflow) {
+                float v[9][3];
 #pragma unroll
-                for (int b = 0; b < 3; ++b) {
-                    const unsigned short sl = cslot[(2 * py + a) * CONV_W + 2 * px + b];
-                    if (sl == CLEAN) { all_dirty = false; continue; }
-                    if (sl < SCRATCH_SLOTS) {
-                        const float* v = scratch + (int)sl * 96 + c3;
-                        m[0] = fmaxf(m[0], __ldcg(v)); m[1] = fmaxf(m[1], __ldcg(v + 1)); m[2] = fmaxf(m[2], __ldcg(v + 2));
+                for (int k = 0; k < 9; ++k) {
+                    const bool ld = sl[k] != CLEAN;
+                    const float* q = scratch + (int)(ld ? sl[k] : 0) * 96 + c3;
+#pragma unroll
+                    for (int j = 0; j < 3; ++j)
+                        v[k][j] = ld ? ((P.flags & 2) ? q[j] : __ldcg(q + j)) : base3[j];   // clean: background
+                }
+#pragma unroll
+                for (int k = 0; k < 9; ++k)
+#pragma unroll
+                    for (int j = 0; j < 3; ++j) m[j] = fmaxf(m[j], v[k][j]);
+            } else {
+                bool all_dirty = true;
+#pragma unroll
+                for (int k = 0; k < 9; ++k) {
+                    if (sl[k] == CLEAN) { all_dirty = false; continue; }
+                    if (sl[k] < SCRATCH_SLOTS) {
+                        const float* v = scratch + (int)sl[k] * 96 + c3;
+                        if (P.flags & 2) {
+                            m[0] = fmaxf(m[0], v[0]); m[1] = fmaxf(m[1], v[1]); m[2] = fmaxf(m[2], v[2]);
+                        } else {
+                            m[0] = fmaxf(m[0], __ldcg(v)); m[1] = fmaxf(m[1], __ldcg(v + 1)); m[2] = fmaxf(m[2], __ldcg(v + 2));
+                        }
                     } else {                             // beyond the scratch capacity: recompute here
                         float v[3];
-                        conv1_at<3>(bm, P, 2 * py + a, 2 * px + b, c3, v);
+                        conv1_at<3>(bm, P, 2 * py + k / 3, 2 * px + (k % 3), c3, v);
                         m[0] = fmaxf(m[0], v[0]); m[1] = fmaxf(m[1], v[1]); m[2] = fmaxf(m[2], v[2]);
                     }
                 }
-            if (!all_dirty) {                                // clean conv positions hold the background value
+                if (!all_dirty) {                            // clean conv positions hold the background value
 #pragma unroll
-                for (int j = 0; j < 3; ++j) m[j] = fmaxf(m[j], base3[j]);
+                    for (int j = 0; j < 3; ++j) m[j] = fmaxf(m[j], base3[j]);
+                }
             }
             lrn3(m, o, lane);
             const long long off =
@@ -310,7 +349,12 @@ int launch_front(const int32_t* rows_dev, long long n, const FrontParams& P, int
     cudaGetDevice(&dev);
     int& blocks_per_sm = blocks_cache[(dev >= 0 && dev < 64) ? dev : 0];
     if (blocks_per_sm == 0) {
-        cudaFuncSetAttribute(front_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+        // 4 CTAs x 38 KB of shared memory fit the 164 KB configuration, which leaves ~90 KB of L1 for
+        // the conv1 weight vectors phase A walks (the channel-0 vectors alone are 46 KB); with the
+        // maximum carve-out L1 was ~25 KB and half of those loads went to L2
+        int carve = 72;
+        if (const char* e = std::getenv("SVX_FRONT_CARVEOUT")) carve = std::atoi(e);
+        cudaFuncSetAttribute(front_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
         int nb = 0;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, front_kernel, bitmap::FRONT_THREADS, 0) !=
                 cudaSuccess || nb < 1)

@@ -476,8 +476,9 @@ int run_cnn(svx_handle* h, long long n, int32_t* labels, float* probs, float* lo
 // rows -> conv2 operand (fused sparse front end) or rows -> conv1 operand (dense path)
 int encode_front(svx_handle* h, const int32_t* rows_dev, long long m, cudaStream_t st) {
     if (h->use_front) {
+        static const int front_flags = [] { const char* e = std::getenv("SVX_FRONT_FLAGS"); return e ? std::atoi(e) : 3; }();
         FrontParams fp{h->front_w255, h->front_base, h->x2_hi, h->x2_lo, h->front_scratch, h->front_blocks,
-                       h->x2_ld, h->x2_group_elems};
+                       h->x2_ld, h->x2_group_elems, front_flags};
         return launch_front(rows_dev, m, fp, h->num_sms, st);
     }
     return launch_encode(rows_dev, m, h->x1, 2, h->num_sms, st);
