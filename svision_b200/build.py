@@ -43,6 +43,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     common = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", *ARCH]
     if verbose:
         common += ["-Xptxas", "-v"]
+    common += os.environ.get("SVX_NVCC_FLAGS", "").split()      # development: e.g. -DSVX_COLLECTOR_A=1
     procs = []
     for src in SOURCES:
         obj = os.path.join(bdir, os.path.splitext(src)[0] + ".o")
