@@ -344,6 +344,56 @@ def call_chromosome(table, labels: np.ndarray, probs: np.ndarray, options, genot
     return [(q, f"{head}\t{gt}:{dr}:{dv}") for (q, head, _, _), (gt, dr, dv) in zip(records, gts)]
 
 
+def region_cuts(table, chunk_rows: int) -> List[int]:
+    """Chunk boundaries ``[0, c1, ..., N]``: about ``chunk_rows`` rows each, cut only where the region
+    column changes (a region is flushed when the next row names another one, predict.py:235-247, so
+    whole chromosomes may be processed chunk by chunk)."""
+    n = len(table)
+    if n == 0:
+        return [0]
+    flags = getattr(table, "flags", None)
+    if flags is not None and len(flags) == n:
+        starts = np.flatnonzero((np.asarray(flags) & 8) == 0)            # SVX_BED_FLAG_SAME_REGION unset
+    else:
+        reg = table.region
+        starts = np.concatenate([[0], 1 + np.flatnonzero(reg[1:] != reg[:-1])])
+    cuts, want = [0], chunk_rows
+    while want < n:
+        k = int(np.searchsorted(starts, want))                            # first region start >= want
+        if k >= len(starts):
+            break
+        c = int(starts[k])
+        if c > cuts[-1]:
+            cuts.append(c)
+        want = c + chunk_rows
+    cuts.append(n)
+    return cuts
+
+
+def call_chromosome_streamed(table, classify: Callable, options, genotype, chunk_rows: int = 65536,
+                             aggregate: Callable = aggregate_region) -> List[Tuple[object, str]]:
+    """:func:`call_chromosome` with the GPU and the host working at the same time: ``classify(rows) ->
+    (labels, probs)`` of chunk k+1 runs on a worker thread (``svx_classify`` releases the GIL) while
+    this thread turns chunk k into records.  Chunks end where the region changes, so the records are
+    exactly those of one ``call_chromosome`` over the whole table."""
+    from concurrent.futures import ThreadPoolExecutor
+    cuts = region_cuts(table, max(int(chunk_rows), 1))
+    spans = list(zip(cuts[:-1], cuts[1:]))
+    if len(spans) <= 1:
+        labels, probs = classify(table.rows)
+        return call_chromosome(table, labels, probs, options, genotype, aggregate)
+    records: list = []
+    with ThreadPoolExecutor(max_workers=1) as pool:
+        pending = pool.submit(classify, np.ascontiguousarray(table.rows[spans[0][0]:spans[0][1]]))
+        for k, (a, b) in enumerate(spans):
+            labels, probs = pending.result()
+            if k + 1 < len(spans):
+                na, nb = spans[k + 1]
+                pending = pool.submit(classify, np.ascontiguousarray(table.rows[na:nb]))
+            records.extend(call_chromosome(table.take(slice(a, b)), labels, probs, options, genotype, aggregate))
+    return records
+
+
 def write_chromosome(out_path_prefix: str, records: List[Tuple[object, str]]) -> None:
     """``<prefix>.vcf`` and ``<prefix>.score.txt`` as ``merge_split_vcfs`` (output.py:307) and
     ``cal_scores_max_min`` (output.py:601-612) expect them."""

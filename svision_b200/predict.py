@@ -96,17 +96,19 @@ def run_predict(segments_out_file: str, out_path_prefix: str, options, aggregate
     clf = classifier if classifier is not None else get_classifier(options.model_path)
     if chrom:
         logging.info("Predicting " + chrom)                           # predict.py:204
-    labels, probs = clf.classify(table.rows)
     if aggregate is None and write is None:
         from . import calls
         if genotype is None:
             contig = chrom if chrom else (str(table.region[0]).split("+")[0] if len(table) else None)
             genotype = calls.AlignmentTable.from_bam(options.bam_path, contig) if contig else (lambda *a: ("./.", 0, 0))
-        records = calls.call_chromosome(table, labels, probs, options, genotype)
+        # classification of the next chunk of regions overlaps the record assembly of this one
+        records = calls.call_chromosome_streamed(table, clf.classify, options, genotype,
+                                                 chunk_rows=getattr(options, "chunk_rows", 65536))
         calls.write_chromosome(out_path_prefix, records)
         return len(records)
     if aggregate is None or write is None:
         raise ValueError("inject both of the reference's aggregate and write functions, or neither")
+    labels, probs = clf.classify(table.rows)
     with open(out_path_prefix + ".score.txt", "w") as score_out, \
             open(out_path_prefix + ".vcf", "w") as vcf_out:
 

@@ -54,6 +54,44 @@ def test_call_chromosome_reproduces_reference_text(golden, tag, opt):
         assert score == str(g[f"{tag}_score"])
 
 
+@pytest.mark.parametrize("chunk_rows", [1, 97, 1000, 10**9])
+def test_streamed_calling_equals_whole_table(golden, chunk_rows):
+    """Chunks cut at region changes, classification of chunk k+1 on a worker thread: same text."""
+    g, table, aln = golden
+    labels, probs = g["labels"], g["probs"]
+    index = {table.rows[i].tobytes(): i for i in range(len(table))}
+    assert len(index) > 0.9 * len(table)
+    calls_seen = []
+
+    def classify(rows):                                   # returns the golden labels of exactly these rows
+        calls_seen.append(rows.shape[0])
+        at0 = next(i for i in range(len(table) - rows.shape[0] + 1)
+                   if i == index.get(rows[0].tobytes(), -1) or np.array_equal(table.rows[i:i + rows.shape[0]], rows))
+        assert np.array_equal(table.rows[at0:at0 + rows.shape[0]], rows)
+        return labels[at0:at0 + rows.shape[0]], probs[at0:at0 + rows.shape[0]]
+
+    opt = G.options(3, True)
+    records = calls.call_chromosome_streamed(table, classify, opt, make_table(aln), chunk_rows=chunk_rows)
+    vcf, score = render(records)
+    assert vcf == str(g["s3_qname_vcf"]) and score == str(g["s3_qname_score"])
+    cuts = calls.region_cuts(table, chunk_rows)
+    assert cuts[0] == 0 and cuts[-1] == len(table) and all(b > a for a, b in zip(cuts, cuts[1:]))
+    assert all(table.region[c] != table.region[c - 1] for c in cuts[1:-1])
+    assert sum(calls_seen) == len(table) and len(calls_seen) == len(cuts) - 1
+    if chunk_rows == 1:
+        assert len(cuts) - 1 == len(set(table.region.tolist()))         # one chunk per region
+
+
+def test_region_cuts_use_parser_flags(tmp_path):
+    from svision_b200 import bed
+    table = sites.make_region_table(3000, seed=77)
+    p = tmp_path / "chr1.segments.all.bed"
+    p.write_text("\n".join(sites.table_to_bed_lines(table)) + "\n")
+    parsed = bed.read_segments_bed(str(p))
+    assert calls.region_cuts(parsed, 500) == calls.region_cuts(table, 500)
+    assert calls.region_cuts(table.take(slice(0, 0)), 10) == [0]
+
+
 def test_write_chromosome_files(golden, tmp_path):
     g, table, aln = golden
     recs = calls.call_chromosome(table, g["labels"], g["probs"], G.options(3, True), make_table(aln).genotype)

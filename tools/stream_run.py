@@ -79,6 +79,15 @@ def main():
     res["records"] = len(records)
     total = a.rows / res["bed_parse_rows_per_s"] + res["classify_s"] + res["alignment_index_s"] + res["calls_s"] + res["write_s"]
     res["pipeline_rows_per_s"] = round(a.rows / total)
+    # the same with GPU classification of chunk k+1 overlapping the record assembly of chunk k
+    # (what predict.run_predict does): identical records
+    t = time.perf_counter()
+    streamed = calls.call_chromosome_streamed(parsed, clf.classify, opt, at)
+    dt = time.perf_counter() - t
+    assert [l for _, l in streamed] == [l for _, l in records]
+    res["streamed_classify_plus_calls_s"] = round(dt, 3)
+    total_s = a.rows / res["bed_parse_rows_per_s"] + dt + res["alignment_index_s"] + res["write_s"]
+    res["pipeline_streamed_rows_per_s"] = round(a.rows / total_s)
     if a.chroms > 0:
         seg_dir, pred_dir = os.path.join(out_dir, "segments"), os.path.join(out_dir, "predict_results")
         os.makedirs(seg_dir, exist_ok=True)
