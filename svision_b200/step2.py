@@ -178,3 +178,86 @@ def run_step2(chroms: Sequence[str], segments_dir: str, predict_dir: str, option
     merged = os.path.join(options.out_path, f"{options.sample}.svision.s{options.min_support}.vcf")
     merge_chromosomes(predict_dir, merged, hi, lo, [c for c in chroms if c in done], options, contigs)
     return merged
+
+
+# ------------------------------------------------------------------------------------------------
+# command line: the reference's flags (SVision:27-106), Step 2 only
+# ------------------------------------------------------------------------------------------------
+def parse_arguments(argv=None):
+    """Same flags, destinations and defaults as the reference driver (``SVision:27-106``), so one
+    command line serves both; flags that only steer Step 1 (collection) are accepted and ignored."""
+    import argparse
+    p = argparse.ArgumentParser(
+        prog="python -m svision_b200.step2",
+        description="SVision Step 2 (CNN prediction, genotyping, merged VCF) on the B200 path.  Expects "
+                    "<out>/segments/<chrom>.segments.all.bed from Step 1 (run the reference with --debug to "
+                    "keep them, or write them with svision_b200.pairs).")
+    io = p.add_argument_group("Input/Output parameters")
+    io.add_argument("-o", dest="out_path", type=os.path.abspath, required=True)
+    io.add_argument("-b", dest="bam_path", type=os.path.abspath, required=True)
+    io.add_argument("-m", dest="model_path", type=os.path.abspath, required=True)
+    io.add_argument("-g", dest="genome", type=os.path.abspath, required=True)
+    io.add_argument("-n", dest="sample", type=str, required=True)
+    opt = p.add_argument_group("Optional parameters")
+    opt.add_argument("-t", dest="thread_num", type=int, default=1)
+    opt.add_argument("-s", dest="min_support", type=int, default=5)
+    opt.add_argument("-c", dest="chrom", type=str, default=None)
+    for flag in ("--hash", "--qname", "--graph", "--contig", "--debug"):
+        opt.add_argument(flag, action="store_true", default=False)
+    col = p.add_argument_group("Collect / cluster / hash parameters (Step 1; accepted for compatibility)")
+    col.add_argument("--min_mapq", type=int, default=10)
+    col.add_argument("--min_sv_size", type=int, default=50)
+    col.add_argument("--max_sv_size", type=int, default=1000000)
+    col.add_argument("--window_size", type=int, default=10000000)
+    col.add_argument("--patition_max_distance", type=int, default=5000)
+    col.add_argument("--cluster_max_distance", type=float, default=0.3)
+    col.add_argument("--k_size", type=int, default=10)
+    col.add_argument("--min_accept", type=int, default=50)
+    col.add_argument("--max_hash_len", type=int, default=1000)
+    pred = p.add_argument_group("Predict / genotype parameters")
+    pred.add_argument("--batch_size", type=int, default=128, help="accepted and ignored: micro-batching is internal")
+    pred.add_argument("--min_gt_depth", type=int, default=4)
+    pred.add_argument("--homo_thresh", type=float, default=0.8)
+    pred.add_argument("--hete_thresh", type=float, default=0.2)
+    pred.add_argument("--device", type=int, default=0, help="CUDA device (not a reference flag)")
+    options = p.parse_args(argv)
+    if options.contig:                                   # SVision:161-162
+        options.min_support = 1
+    return options
+
+
+def chromosomes_with_segments(segments_dir: str, contigs: Sequence[Tuple[str, int]], only: Optional[str] = None):
+    """Chromosomes that have a segments file, in the genome's contig order (the reference walks the
+    FASTA's contigs, ``SVision:167-234``); ``only`` = the ``-c`` flag (``chr1`` or ``chr1:a-b``)."""
+    want = only.split(":")[0] if only else None
+    return [name for name, _ in contigs
+            if (want is None or name == want) and os.path.exists(os.path.join(segments_dir, name + ".segments.all.bed"))]
+
+
+def main(argv=None, classifier=None, genotype_for: Optional[Callable] = None) -> int:
+    options = parse_arguments(argv)
+    logging.basicConfig(level=logging.INFO, format="%(asctime)s %(message)s")
+    segments_dir = os.path.join(options.out_path, "segments")
+    predict_dir = os.path.join(options.out_path, "predict_results")
+    contigs = contigs_from_fai(options.genome)
+    chroms = chromosomes_with_segments(segments_dir, contigs, options.chrom)
+    if not chroms:
+        logging.error("no <chrom>.segments.all.bed under %s", segments_dir)
+        return 1
+    if classifier is None:
+        classifier = _predict.get_classifier(options.model_path, device=options.device)
+    try:
+        merged = run_step2(chroms, segments_dir, predict_dir, options, classifier, genotype_for, contigs)
+    except ValueError as e:                               # 'Empty output in the score file' (SVision:374-376)
+        logging.error("%s", e)
+        return 1
+    logging.info("[Prediction finished] %d chromosome(s) -> %s", len(chroms), merged)
+    if not options.debug:                                 # SVision:370-372 removes the intermediates
+        import shutil
+        shutil.rmtree(predict_dir, ignore_errors=True)
+    return 0
+
+
+if __name__ == "__main__":
+    import sys
+    sys.exit(main())

@@ -138,3 +138,25 @@ def test_merge_is_byte_identical_to_the_reference(tmp_path, graph):
     assert open(merged, "rb").read() == open(ref_path, "rb").read()
     if not graph:                                       # the committed digest is of this very text
         assert hashlib.sha256(open(merged, "rb").read()).hexdigest() == open(GOLDEN_SHA).read().split()[0]
+
+
+def test_command_line_runs_step2_with_the_reference_flags(tmp_path):
+    seg_dir, _, clf, tables = _prepare(tmp_path, chroms=("chr2", "chr1"))       # files exist for chr1, chr2
+    os.rename(seg_dir, str(tmp_path / "out_segments_tmp"))
+    out = tmp_path / "out"
+    out.mkdir()
+    os.rename(str(tmp_path / "out_segments_tmp"), str(out / "segments"))
+    argv = ["-o", str(out), "-b", "synthetic.bam", "-m", "unused.ckpt", "-g", str(tmp_path / "genome.fa"),
+            "-n", "NA12878", "-s", "2", "--qname", "--debug", "-t", "8", "--batch_size", "128", "--window_size", "5000000"]
+    assert step2.main(argv, classifier=clf, genotype_for=tables.get) == 0
+    merged = out / "NA12878.svision.s2.vcf"
+    body = [l.split("\t") for l in merged.read_text().split("\n") if l and not l.startswith("#")]
+    assert [r[0] for r in body] == sorted((r[0] for r in body), key=["chr1", "chr2"].index)   # .fai order
+    assert {r[0] for r in body} == {"chr1", "chr2"} and "READS=" in body[0][7]
+    assert (out / "predict_results" / "chr1.predict.s2.vcf").exists()                          # --debug keeps them
+    # -c restricts, --contig forces min_support 1, intermediates are removed without --debug
+    argv2 = [a for a in argv if a != "--debug"] + ["-c", "chr2:1-1000", "--contig"]
+    assert step2.main(argv2, classifier=clf, genotype_for=tables.get) == 0
+    body2 = [l.split("\t") for l in (out / "NA12878.svision.s1.vcf").read_text().split("\n") if l and not l.startswith("#")]
+    assert {r[0] for r in body2} == {"chr2"} and not (out / "predict_results").exists()
+    assert step2.main(argv + ["-c", "chr9"], classifier=clf, genotype_for=tables.get) == 1
