@@ -218,6 +218,29 @@ int svx_pairs_generate(int64_t n_sig, const int64_t *sig_aln_off, const int64_t 
                        const int64_t *sig_bkp_off, int64_t capacity, int32_t *rows, int64_t *meta,
                        int64_t *n_rows);
 
+/* ---- host side: labels -> candidate SVs per region (no GPU involved) -----------------------------
+ * Replaces, for one chromosome, the per-row loop of Predict.run (src/network/predict.py:213-300),
+ * Predict.get_region_potential_svtypes (predict.py:29-145) and the numeric part of
+ * write_results_to_vcf (src/network/output.py:473-474,495-496,525-529,551-552).  Inputs are what
+ * svx_bed_parse produced (text, spans, flags, the three breakpoint columns) plus the classifier's
+ * labels and `win[i]` = round(softmax of the label, 2) as float32 (predict.py:251).
+ *   cand   [capacity n][25] int64  per emitted candidate (support >= min_support), in file order:
+ *            0 first kept row of its region, 1 support, 2 number of classes, 3 1 = filter "Uncovered",
+ *            4 offset into `reads`, 5..9 class ids ascending, 10..24 breakpoints [class][start,end,len]
+ *   qual   [capacity n] double     std(signature scores) / support + (1 - round(mean(win), 2)) * 100,
+ *                                  before the min with 100 (output.py:474,551-552)
+ *   reads  [capacity n] int64      per supporting read the LAST row that named it (its qname and
+ *                                  signature score are that row's: predict.py:249,255)
+ * numpy.mean over float32 and numpy.std over ints are restated operation by operation, because the
+ * values are printed; svx_np_mean_f32 / svx_np_std_i64 expose the two for the parity tests. */
+#define SVX_CAND_FIELDS 25
+int svx_calls_aggregate(const char *text, int64_t len, int64_t n, const int64_t *spans, const int32_t *flags,
+                        const int64_t *bkp_start, const int64_t *bkp_end, const int64_t *bkp_len,
+                        const int32_t *labels, const float *win, int64_t min_support, int64_t *cand,
+                        double *qual, int64_t *reads, int64_t *n_cand, int64_t *n_reads);
+int svx_np_mean_f32(const float *values, int64_t n, float *out);
+int svx_np_std_i64(const int64_t *values, int64_t n, double *out);
+
 int64_t svx_max_batch(const svx_handle *h);
 int svx_device(const svx_handle *h);
 const char *svx_last_error(void);

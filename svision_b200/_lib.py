@@ -20,6 +20,7 @@ SYMBOLS = (
     "svx_bed_count_rows", "svx_bed_parse", "svx_pairs_generate",
     "svx_classify_device_calls", "svx_exchange_create", "svx_exchange_export", "svx_exchange_attach",
     "svx_classify_exchange", "svx_exchange_status", "svx_exchange_destroy",
+    "svx_calls_aggregate", "svx_np_mean_f32", "svx_np_std_i64",
 )
 IPC_HANDLE_BYTES = 64
 
@@ -94,6 +95,13 @@ def load() -> ctypes.CDLL:
     lib.svx_exchange_status.restype = i32
     lib.svx_exchange_destroy.argtypes = [vp]
     lib.svx_exchange_destroy.restype = None
+    lib.svx_calls_aggregate.argtypes = [vp, i64, i64, vp, vp, vp, vp, vp, vp, vp, i64, vp, vp, vp,
+                                        ctypes.POINTER(i64), ctypes.POINTER(i64)]
+    lib.svx_calls_aggregate.restype = i32
+    lib.svx_np_mean_f32.argtypes = [vp, i64, vp]
+    lib.svx_np_mean_f32.restype = i32
+    lib.svx_np_std_i64.argtypes = [vp, i64, vp]
+    lib.svx_np_std_i64.restype = i32
     lib.svx_max_batch.argtypes = [vp]
     lib.svx_max_batch.restype = i64
     lib.svx_device.argtypes = [vp]

@@ -83,9 +83,35 @@ class SegmentsTable:
         return out
 
     def take(self, index) -> "SegmentsTable":
-        """Row subset (slice or index array) with materialised string columns."""
+        """Row subset (slice or index array).  A parsed table keeps pointing into its text (string
+        columns stay lazy); otherwise the string columns are materialised."""
+        if self._text is not None:
+            return SegmentsTable(self.rows[index], self.bkp_start[index], self.bkp_end[index], self.bkp_len[index],
+                                 flags=self.flags[index], text=self._text, spans=self._spans[index],
+                                 **{k: v[index] for k, v in self._cols.items()})
         return SegmentsTable(self.rows[index], self.bkp_start[index], self.bkp_end[index], self.bkp_len[index],
                              **{k: getattr(self, k)[index] for k in _SPAN_OF})
+
+    def has_text(self) -> bool:
+        """True for a table parsed from BED text (byte spans available to the native host steps)."""
+        return self._text is not None and self._spans is not None
+
+    def strings_at(self, name: str, rows) -> list:
+        """Cells of a string column at ``rows`` (index array) as a list, decoding only those."""
+        col = self._cols.get(name)
+        if col is not None:
+            return [str(x) for x in col[rows].tolist()]
+        sp = self._spans[rows, _SPAN_OF[name]]
+        text = self._text
+        return [text[o:o + n].decode() for o, n in zip(sp[:, 0].tolist(), sp[:, 1].tolist())]
+
+    def string_at(self, name: str, row: int) -> str:
+        """One cell of a string column without decoding the whole column."""
+        col = self._cols.get(name)
+        if col is not None:
+            return str(col[row])
+        off, ln = self._spans[row, _SPAN_OF[name]]
+        return self._text[off:off + ln].decode()
 
     def label_strings(self) -> list:
         """The reference's per-row label strings (create_batch.py:48), for compatibility."""

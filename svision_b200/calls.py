@@ -27,6 +27,7 @@ from typing import Callable, Iterable, List, Optional, Sequence, Tuple
 import numpy as np
 
 TYPE_NAMES = ("DEL", "INS", "INV", "DUP", "tDUP")            # predict.py:133-142
+USE_NATIVE = True          # svx_calls_aggregate for tables parsed from BED text (tests switch it off to compare)
 MAX_GENOTYPE_ALIGNMENTS = 500                                 # genotype.py:34
 
 
@@ -264,14 +265,69 @@ def pending_records(candidates: list, region: str, read_names: dict, sig_types: 
         names = [read_names[r] for r in read_ids]
         spread = np.std([int(sig_scores[r]) for r in read_ids]) / support          # output.py:551
         qual = min(100, spread + class_penalty)
-        kinds, kb = refine_types(kinds_str.split("+"), bkps, options.min_sv_size)
-        info = [f"END={end}", f"SVLEN={end - start}", "SVTYPE=" + "+".join(kinds), f"SUPPORT={support}",
-                "BKPS=" + ",".join(f"{k}:{b[2]}-{b[0]}-{b[1]}" for k, b in zip(kinds, kb))]
-        if options.qname:
-            info.append("READS=" + ",".join(names))
-        alt = "<CSV>" if len(kinds) >= 2 else "<SV>"                  # output.py:573-576
-        out.append((qual, "\t".join([contig, str(start), "0", "N", alt, str(qual), flt, ";".join(info), "GT:DR:DV"]),
-                    (contig, start, end, kinds), names))
+        out.append(_record(contig, start, end, kinds_str.split("+"), bkps, support, names, qual, flt, options))
+    return out
+
+
+def _record(contig: str, start: int, end: int, kinds: list, bkps: list, support: int, names: list, qual,
+            flt: str, options) -> tuple:
+    """One pending record ``(qual, line_without_sample_column, candidate, supporting_read_names)``
+    (output.py:553-598: type refinement, INFO fields, ALT)."""
+    kinds, kb = refine_types(kinds, bkps, options.min_sv_size)
+    info = [f"END={end}", f"SVLEN={end - start}", "SVTYPE=" + "+".join(kinds), f"SUPPORT={support}",
+            "BKPS=" + ",".join(f"{k}:{b[2]}-{b[0]}-{b[1]}" for k, b in zip(kinds, kb))]
+    if options.qname:
+        info.append("READS=" + ",".join(names))
+    alt = "<CSV>" if len(kinds) >= 2 else "<SV>"                      # output.py:573-576
+    return (qual, "\t".join([contig, str(start), "0", "N", alt, str(qual), flt, ";".join(info), "GT:DR:DV"]),
+            (contig, start, end, kinds), names)
+
+
+def pending_records_native(table, labels: np.ndarray, win: np.ndarray, options) -> Optional[list]:
+    """All pending records of a chromosome through ``svx_calls_aggregate`` (``csrc/host_calls.cpp``):
+    the per-row loop, the aggregation and the score arithmetic run natively over the parser's byte
+    spans, and Python only formats the candidates that reached ``min_support``.  Returns ``None`` when
+    the native step declines (e.g. a signature score that only Python's ``int()`` accepts), so the
+    caller can take the pure-Python route."""
+    from . import _lib
+    lib = _lib.load()
+    n = len(table)
+    if n == 0:
+        return []
+    import ctypes
+    text, spans = table._text, np.ascontiguousarray(table._spans, dtype=np.int64)
+    flags = np.ascontiguousarray(table.flags, dtype=np.int32)
+    b0 = np.ascontiguousarray(table.bkp_start, dtype=np.int64)
+    b1 = np.ascontiguousarray(table.bkp_end, dtype=np.int64)
+    b2 = np.ascontiguousarray(table.bkp_len, dtype=np.int64)
+    labels = np.ascontiguousarray(labels, dtype=np.int32)
+    win = np.ascontiguousarray(win, dtype=np.float32)
+    cand = np.empty((n, 25), dtype=np.int64)
+    qual = np.empty(n, dtype=np.float64)
+    reads = np.empty(n, dtype=np.int64)
+    nc, nr = ctypes.c_int64(0), ctypes.c_int64(0)
+    rc = lib.svx_calls_aggregate(text, len(text), n, spans.ctypes.data, flags.ctypes.data, b0.ctypes.data,
+                                 b1.ctypes.data, b2.ctypes.data, labels.ctypes.data, win.ctypes.data,
+                                 int(options.min_support), cand.ctypes.data, qual.ctypes.data, reads.ctypes.data,
+                                 ctypes.byref(nc), ctypes.byref(nr))
+    if rc != 0:
+        return None
+    out = []
+    region_cache = (-1, None)
+    cand_l = cand[:nc.value].tolist()
+    all_names = table.strings_at("read_name", reads[:nr.value])        # decoded once, for the emitted candidates only
+    region_of = dict(zip(*(lambda r: (r.tolist(), table.strings_at("region", r)))(np.unique(cand[:nc.value, 0]))))
+    for c, q in zip(cand_l, qual[:nc.value]):                           # q stays numpy.float64: str() prints like the reference
+        row, support, nk, uncovered, roff = c[:5]
+        if region_cache[0] != row:
+            contig, start, end = region_of[row].split("+")[:3]
+            region_cache = (row, (contig, int(start), int(end)))
+        contig, start, end = region_cache[1]
+        kinds = [TYPE_NAMES[k] for k in c[5:5 + nk]]
+        bkps = [c[10 + 3 * k:13 + 3 * k] for k in range(nk)]
+        names = all_names[roff:roff + support]
+        out.append(_record(contig, start, end, kinds, bkps, support, names, min(100, q),
+                           "Uncovered" if uncovered else "PASS", options))
     return out
 
 
@@ -291,9 +347,13 @@ def call_chromosome(table, labels: np.ndarray, probs: np.ndarray, options, genot
     assert probs.dtype == np.float32, "scores must stay numpy.float32 (SURVEY §8(b))"
     n = len(table)
     pred_arr = np.asarray(labels).astype(np.int64)
-    pred = pred_arr.tolist()
     # round(np.float32, 2) of the winning class, elementwise the same ufunc as numpy.round
     win = np.round(probs[np.arange(n), pred_arr], 2) if n else np.zeros(0, np.float32)
+    if aggregate is aggregate_region and getattr(table, "has_text", lambda: False)() and USE_NATIVE:
+        records = pending_records_native(table, pred_arr, win, options)
+        if records is not None:
+            return _genotyped(records, genotype, options)
+    pred = pred_arr.tolist()
     fwd_inv = ((table.forward == "True") & (pred_arr == 2)).tolist() if n else []
     read_num, region_col, read_name = table.read_num.tolist(), table.region.tolist(), table.read_name.tolist()
     sig_type, sig_score, mech = table.sig_type.tolist(), table.sig_score.tolist(), table.mechanism.tolist()
@@ -337,6 +397,10 @@ def call_chromosome(table, labels: np.ndarray, probs: np.ndarray, options, genot
         else:
             slot[p] = [b0[i], b1[i], b2[i]]
     flush()                                                           # predict.py:298-300
+    return _genotyped(records, genotype, options)
+
+
+def _genotyped(records: list, genotype, options) -> List[Tuple[object, str]]:
     if hasattr(genotype, "genotype_many"):
         gts = genotype.genotype_many([r[2] for r in records], [r[3] for r in records], options)
     else:

@@ -92,6 +92,80 @@ def test_region_cuts_use_parser_flags(tmp_path):
     assert calls.region_cuts(table.take(slice(0, 0)), 10) == [0]
 
 
+def _parsed(table, tmp_path):
+    from svision_b200 import bed
+    p = tmp_path / "chr1.segments.all.bed"
+    p.write_text("\n".join(sites.table_to_bed_lines(table)) + "\n")
+    return bed.read_segments_bed(str(p))
+
+
+@pytest.mark.parametrize("tag,opt", [("s3_qname", G.options(3, True)), ("s1", G.options(1, False)),
+                                     ("s5_min200", G.options(5, False, 200))])
+def test_native_aggregation_reproduces_reference_text(golden, tag, opt, tmp_path, monkeypatch):
+    """The same golden text through ``svx_calls_aggregate`` (table parsed from BED text), whole and in
+    chunks, and the pure-Python route on the same parsed table."""
+    g, table, aln = golden
+    parsed = _parsed(table, tmp_path)
+    assert parsed.has_text() and not table.has_text()
+    at = make_table(aln)
+    used = []
+    real = calls.pending_records_native
+    monkeypatch.setattr(calls, "pending_records_native", lambda *a: used.append(1) or real(*a))
+    vcf, score = render(calls.call_chromosome(parsed, g["labels"], g["probs"], opt, at))
+    assert used and vcf == str(g[f"{tag}_vcf"]) and score == str(g[f"{tag}_score"])
+    index = {parsed.rows[i].tobytes(): i for i in range(len(parsed))}
+
+    def classify(rows):
+        i0 = index[rows[0].tobytes()]
+        while not np.array_equal(parsed.rows[i0:i0 + rows.shape[0]], rows):
+            i0 = next(i for i in range(i0 + 1, len(parsed)) if np.array_equal(parsed.rows[i], rows[0]))
+        return g["labels"][i0:i0 + rows.shape[0]], g["probs"][i0:i0 + rows.shape[0]]
+
+    n_used = len(used)
+    vcf2, score2 = render(calls.call_chromosome_streamed(parsed, classify, opt, at, chunk_rows=700))
+    assert len(used) > n_used + 3 and vcf2 == vcf and score2 == score
+    monkeypatch.setattr(calls, "USE_NATIVE", False)
+    n_used = len(used)
+    vcf3, score3 = render(calls.call_chromosome(parsed, g["labels"], g["probs"], opt, at))
+    assert len(used) == n_used and vcf3 == vcf and score3 == score
+
+
+def test_native_numpy_reductions_match_numpy():
+    """numpy.mean over float32 scores and numpy.std over integer signature scores, restated in
+    csrc/host_calls.cpp, against numpy itself (they end up printed: output.py:473-474,551)."""
+    import ctypes
+    from svision_b200 import _lib
+    lib = _lib.load()
+    rng = np.random.default_rng(5)
+    for trial in range(4000):
+        n = int(rng.integers(1, 300)) if trial % 20 else int(rng.integers(300, 30000))
+        a = np.round(rng.random(n).astype(np.float32), 2)
+        out = np.zeros(1, np.float32)
+        assert lib.svx_np_mean_f32(a.ctypes.data, n, out.ctypes.data) == 0
+        assert out[0] == (np.mean(list(a)) if n < 300 else np.mean(a)), n
+        b = rng.integers(-50, 5000, size=n).astype(np.int64)
+        o2 = np.zeros(1, np.float64)
+        assert lib.svx_np_std_i64(b.ctypes.data, n, o2.ctypes.data) == 0
+        assert o2[0] == (np.std([int(x) for x in b]) if n < 300 else np.std(b)), n
+    assert lib.svx_np_mean_f32(None, 0, None) != 0
+
+
+def test_native_aggregation_declines_what_only_python_parses(golden, tmp_path, monkeypatch):
+    g, table, aln = golden
+    lines = sites.table_to_bed_lines(table.take(slice(0, 200)))
+    cols = lines[5].split("\t")
+    cols[19] = " 7 "                                       # int(' 7 ') is fine in Python; the native parser declines
+    lines[5] = "\t".join(cols)
+    from svision_b200 import bed
+    parsed = bed.parse_segments_bed(("\n".join(lines) + "\n").encode())
+    win = np.round(g["probs"][np.arange(200), g["labels"][:200]], 2)
+    assert calls.pending_records_native(parsed, g["labels"][:200], win, G.options(1, False)) is None
+    recs = calls.call_chromosome(parsed, g["labels"][:200], g["probs"][:200], G.options(1, False), make_table(aln))
+    monkeypatch.setattr(calls, "USE_NATIVE", False)      # the same table through the pure-Python route
+    calls_py = calls.call_chromosome(parsed, g["labels"][:200], g["probs"][:200], G.options(1, False), make_table(aln))
+    assert [l for _, l in recs] == [l for _, l in calls_py] and len(recs) > 3
+
+
 def test_write_chromosome_files(golden, tmp_path):
     g, table, aln = golden
     recs = calls.call_chromosome(table, g["labels"], g["probs"], G.options(3, True), make_table(aln).genotype)
@@ -207,3 +281,9 @@ def test_call_chromosome_live_vs_reference(seed):
     got_vcf, got_score = render(calls.call_chromosome(table, labels, probs, opt, make_table(aln)))
     assert got_vcf == vcf and got_score == score
     assert opens == vcf.count("\n") > 50           # the reference re-opens the BAM once per record
+    import tempfile
+    with tempfile.TemporaryDirectory() as d:        # the native route (table parsed from BED text)
+        import pathlib
+        parsed = _parsed(table, pathlib.Path(d))
+        nat_vcf, nat_score = render(calls.call_chromosome(parsed, labels, probs, opt, make_table(aln)))
+    assert nat_vcf == vcf and nat_score == score

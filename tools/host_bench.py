@@ -49,8 +49,14 @@ def main():
     t = time.perf_counter()
     recs = calls.call_chromosome(table, labels, probs, opt, at)
     dt = time.perf_counter() - t
-    out.update(records=len(recs), alignment_index_s=round(t_index, 3), calls_rows_per_s=round(a.rows / dt),
-               calls_s=round(dt, 3))
+    out.update(records=len(recs), alignment_index_s=round(t_index, 3), calls_python_rows_per_s=round(a.rows / dt),
+               calls_python_s=round(dt, 3))
+    # the production route: table parsed from BED text -> svx_calls_aggregate (csrc/host_calls.cpp)
+    t = time.perf_counter()
+    recs_native = calls.call_chromosome(parsed, labels, probs, opt, at)
+    dn = time.perf_counter() - t
+    assert [l for _, l in recs_native] == [l for _, l in recs], "native aggregation differs from the Python route"
+    out.update(calls_rows_per_s=round(a.rows / dn), calls_s=round(dn, 3))
     if a.reference:
         t = time.perf_counter()
         vcf, _, opens = G.reference_text(table, labels, probs, aln, opt)
