@@ -234,6 +234,14 @@ int setup_layer(svx_handle* h, int li, const __half* a_hi, const __half* a_lo, l
     int rc;
     L.block_n = s.block_n;
     L.chunk_kblocks = chunk_kblocks();
+    if (li == L_CONV3 || li == L_CONV4) {
+        // 192-column tiles have only two TMEM buffers, and their per-tile store phase (~9.3k clk) is
+        // longer than two 4-block chunks of MMA work (9.2k clk): the MMA warp waited 140-170 clk per
+        // k-block for a free buffer.  Chunks of 6 k-blocks (K = 384) let it run 13.8k clk ahead:
+        // 1242 -> 1155 clk per k-block (99.7 % of the issue bound) for max |dsoftmax| 1.08e-4 -> 1.33e-4
+        if (!std::getenv("SVX_CHUNK")) L.chunk_kblocks = 6;
+        if (const char* e = std::getenv("SVX_CHUNK34")) { const int v = std::atoi(e); if (v >= 1 && v <= 64) L.chunk_kblocks = v; }
+    }
     L.groups = s.groups;
     L.n_per_group = s.n_total / s.groups;
     L.taps = s.taps;
