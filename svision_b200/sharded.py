@@ -59,6 +59,24 @@ def classify_sharded(classify_fn, rows: np.ndarray, device=None, group=None):
     return fl.cpu().numpy(), fp.cpu().numpy()
 
 
+class ShardedClassifier:
+    """``classify(rows)`` over all ranks: every rank holds its own classifier (one GPU each), takes the
+    contiguous shard of ``rows`` that :func:`shard_rows` gives it and gets the full-length results back
+    (:func:`classify_sharded`: one all-gather).  Every rank must make the same calls with the same rows
+    -- ``svision_b200.step2`` under ``torchrun`` does."""
+
+    def __init__(self, local, group=None):
+        self.local, self.group = local, group
+        dev = getattr(local, "torch_device", None)
+        self.device = dev if (dev is not None and dist.get_backend(group) == "nccl") else torch.device("cpu")
+
+    def classify(self, rows):
+        rows = np.ascontiguousarray(rows, dtype=np.int32)
+        if rows.shape[0] == 0:
+            return np.empty((0,), np.int32), np.empty((0, 5), np.float32)
+        return classify_sharded(self.local.classify, rows, device=self.device, group=self.group)
+
+
 class _DeviceView:
     """A library-owned device buffer exposed through ``__cuda_array_interface__`` (zero copy)."""
 

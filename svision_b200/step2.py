@@ -244,17 +244,45 @@ def main(argv=None, classifier=None, genotype_for: Optional[Callable] = None) ->
     if not chroms:
         logging.error("no <chrom>.segments.all.bed under %s", segments_dir)
         return 1
+    # under torchrun (one process per GPU) the rows of every chunk are sharded over the ranks; every
+    # rank walks the same chromosomes so that the collectives line up, rank 0 owns the output files
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    scratch = None
+    if world > 1:
+        import tempfile
+        import torch
+        import torch.distributed as dist
+        from . import sharded
+        if not dist.is_initialized():
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            dist.init_process_group("nccl" if (classifier is None and torch.cuda.is_available()) else "gloo")
+        if classifier is None:
+            options.device = int(os.environ.get("LOCAL_RANK", rank))
+        if rank != 0:                                     # same work, throw-away files, no BAM reads
+            scratch = tempfile.mkdtemp(prefix=f"svx_step2_rank{rank}_")
+            predict_dir = os.path.join(scratch, "predict_results")
+            options.out_path = scratch
+            if genotype_for is None:
+                genotype_for = lambda chrom: (lambda *a: ("./.", 0, 0))    # noqa: E731
     if classifier is None:
         classifier = _predict.get_classifier(options.model_path, device=options.device)
+    if world > 1:
+        classifier = sharded.ShardedClassifier(classifier)
     try:
         merged = run_step2(chroms, segments_dir, predict_dir, options, classifier, genotype_for, contigs)
     except ValueError as e:                               # 'Empty output in the score file' (SVision:374-376)
         logging.error("%s", e)
         return 1
-    logging.info("[Prediction finished] %d chromosome(s) -> %s", len(chroms), merged)
-    if not options.debug:                                 # SVision:370-372 removes the intermediates
-        import shutil
-        shutil.rmtree(predict_dir, ignore_errors=True)
+    finally:
+        if scratch is not None:
+            import shutil
+            shutil.rmtree(scratch, ignore_errors=True)
+    if rank == 0:
+        logging.info("[Prediction finished] %d chromosome(s) on %d GPU(s) -> %s", len(chroms), world, merged)
+        if not options.debug:                             # SVision:370-372 removes the intermediates
+            import shutil
+            shutil.rmtree(predict_dir, ignore_errors=True)
     return 0
 
 

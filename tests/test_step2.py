@@ -160,3 +160,56 @@ def test_command_line_runs_step2_with_the_reference_flags(tmp_path):
     body2 = [l.split("\t") for l in (out / "NA12878.svision.s1.vcf").read_text().split("\n") if l and not l.startswith("#")]
     assert {r[0] for r in body2} == {"chr2"} and not (out / "predict_results").exists()
     assert step2.main(argv + ["-c", "chr9"], classifier=clf, genotype_for=tables.get) == 1
+
+
+class HashClassifier:
+    """Deterministic per-row results (any shard of any batch gives the same answer for a row)."""
+
+    def classify(self, rows):
+        rows = np.ascontiguousarray(rows, dtype=np.int64)
+        h = (rows * np.arange(1, 13, dtype=np.int64)).sum(1)
+        labels = (np.abs(h) % 5).astype(np.int32)
+        probs = np.full((rows.shape[0], 5), 0.05, dtype=np.float32)
+        probs[np.arange(rows.shape[0]), labels] = (0.6 + (np.abs(h) % 37) / 100.0).astype(np.float32)
+        return labels, probs
+
+
+def _step2_worker(rank, world, port, argv, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    import torch.distributed as dist
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    rc = step2.main(argv, classifier=HashClassifier(), genotype_for=lambda chrom: (lambda *a: ("0/1", 3, 4)))
+    q.put((rank, rc))
+    dist.destroy_process_group()
+
+
+def test_command_line_under_torchrun_shards_rows_over_ranks_gloo_world2(tmp_path):
+    """Two ranks (gloo, CPU): every chunk's rows are sharded over the ranks, rank 0 writes the files;
+    the merged VCF equals the single-process run."""
+    import torch.multiprocessing as mp
+    seg_dir, _, _, _ = _prepare(tmp_path)
+    outs = {}
+    for name in ("single", "sharded"):
+        out = tmp_path / name
+        (out / "segments").mkdir(parents=True)
+        for f in os.listdir(seg_dir):
+            (out / "segments" / f).write_bytes(open(os.path.join(seg_dir, f), "rb").read())
+        outs[name] = out
+    argv = lambda out: ["-o", str(out), "-b", "x.bam", "-m", "x.ckpt", "-g", str(tmp_path / "genome.fa"),   # noqa: E731
+                        "-n", "S", "-s", "2", "--qname"]
+    assert step2.main(argv(outs["single"]), classifier=HashClassifier(),
+                      genotype_for=lambda chrom: (lambda *a: ("0/1", 3, 4))) == 0
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 500) + 333
+    procs = [ctx.Process(target=_step2_worker, args=(r, 2, port, argv(outs["sharded"]), q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=180) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+    assert res == [(0, 0), (1, 0)]
+    a = (outs["single"] / "S.svision.s2.vcf").read_text()
+    b = (outs["sharded"] / "S.svision.s2.vcf").read_text()
+    assert a == b and a.count("\n") > 100

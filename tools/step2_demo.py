@@ -1,0 +1,80 @@
+"""Whole Step 2 through the command-line entry, on 1 or N GPUs:
+
+    python tools/step2_demo.py [--rows 200000] [--chroms 3]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29521 \
+        tools/step2_demo.py --rows 200000 --chroms 3
+
+Rank 0 prepares <out>/segments/<chrom>.segments.all.bed (synthetic region-grouped streams), a genome
+.fai and a TF-format checkpoint of the synthetic weights (written with svision_b200.tf_bundle, read back
+through the -m loader, so the TF-free reader is on the path), then every rank runs
+``svision_b200.step2.main`` with the reference's flags.  Genotypes come from synthetic alignment tables
+(reading a real BAM needs pysam, as in the reference).  Prints one JSON line on rank 0: rows/s of the
+whole step and the digest of the merged VCF (equal for every world size)."""
+import argparse
+import hashlib
+import json
+import os
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from svision_b200 import calls, sites, step2, tf_bundle, weights  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--rows", type=int, default=200_000, help="rows per chromosome")
+    ap.add_argument("--chroms", type=int, default=3)
+    ap.add_argument("--out", default=None)
+    a = ap.parse_args()
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    out = a.out or os.path.join(tempfile.gettempdir(), "svx_step2_demo")
+    names = [f"chr{k + 1}" for k in range(a.chroms)]
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", rank)))
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl")
+    tables = {}
+    for k, chrom in enumerate(names):                    # every rank builds the same streams (seeded)
+        tables[chrom] = sites.make_region_table(a.rows, seed=sites.SEED_CONFIG4 + 10 * k, contig=chrom)
+    if rank == 0:
+        os.makedirs(os.path.join(out, "segments"), exist_ok=True)
+        for chrom, t in tables.items():
+            with open(os.path.join(out, "segments", chrom + ".segments.all.bed"), "w") as f:
+                f.write("\n".join(sites.table_to_bed_lines(t)) + "\n")
+        with open(os.path.join(out, "genome.fa.fai"), "w") as f:
+            f.writelines(f"{c}\t250000000\t0\t70\t71\n" for c in names)
+        tf_bundle.write_bundle(os.path.join(out, "model.ckpt"), weights.synthetic_weights())
+    if world > 1:
+        dist.barrier()
+    aligns = {}
+    if rank == 0:
+        for k, chrom in enumerate(names):
+            al = sites.make_alignments(tables[chrom], seed=7 + k)
+            aligns[chrom] = calls.AlignmentTable(al["contig_length"], al["reference_start"], al["reference_end"],
+                                                 al["mapping_quality"], al["is_unmapped"], al["is_secondary"],
+                                                 al["query_name"])
+    argv = ["-o", out, "-b", "synthetic.bam", "-m", os.path.join(out, "model.ckpt"), "-g", os.path.join(out, "genome.fa"),
+            "-n", "demo", "-s", "3", "--debug"]
+    t = time.perf_counter()
+    rc = step2.main(argv, genotype_for=aligns.get if rank == 0 else None)
+    dt = time.perf_counter() - t
+    if rank == 0:
+        merged = os.path.join(out, "demo.svision.s3.vcf")
+        text = open(merged, "rb").read()
+        print(json.dumps({"world": world, "rc": rc, "chromosomes": a.chroms, "rows": a.rows * a.chroms,
+                          "step2_s": round(dt, 3), "rows_per_s": round(a.rows * a.chroms / dt),
+                          "records": sum(1 for l in text.split(b"\n") if l and not l.startswith(b"#")),
+                          "merged_sha256": hashlib.sha256(text).hexdigest()}), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return rc
+
+
+if __name__ == "__main__":
+    sys.exit(main())
