@@ -61,14 +61,19 @@ def main():
                                                  al["query_name"])
     argv = ["-o", out, "-b", "synthetic.bam", "-m", os.path.join(out, "model.ckpt"), "-g", os.path.join(out, "genome.fa"),
             "-n", "demo", "-s", "3", "--debug"]
+    from svision_b200 import predict
+    t = time.perf_counter()                                # -m loader (TF bundle, no TF) + weight repack + workspaces
+    clf = predict.get_classifier(os.path.join(out, "model.ckpt"), device=int(os.environ.get("LOCAL_RANK", rank)))
+    clf.classify(tables[names[0]].rows[:4096])             # first-launch warm-up
+    t_model = time.perf_counter() - t
     t = time.perf_counter()
-    rc = step2.main(argv, genotype_for=aligns.get if rank == 0 else None)
+    rc = step2.main(argv, classifier=clf, genotype_for=aligns.get if rank == 0 else None)
     dt = time.perf_counter() - t
     if rank == 0:
         merged = os.path.join(out, "demo.svision.s3.vcf")
         text = open(merged, "rb").read()
         print(json.dumps({"world": world, "rc": rc, "chromosomes": a.chroms, "rows": a.rows * a.chroms,
-                          "step2_s": round(dt, 3), "rows_per_s": round(a.rows * a.chroms / dt),
+                          "model_load_s": round(t_model, 3), "step2_s": round(dt, 3), "rows_per_s": round(a.rows * a.chroms / dt),
                           "records": sum(1 for l in text.split(b"\n") if l and not l.startswith(b"#")),
                           "merged_sha256": hashlib.sha256(text).hexdigest()}), flush=True)
     if world > 1:
