@@ -74,6 +74,23 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     }
 }
 
+// The same on a precomputed shared::cta address (hot loops keep barrier addresses in registers)
+__device__ __forceinline__ void mbar_wait_addr(uint32_t bar_addr, uint32_t parity) {
+    uint32_t spins = 0;
+    for (;;) {
+        uint32_t ok;
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.b32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(bar_addr), "r"(parity)
+            : "memory");
+        if (ok) break;
+        if (++spins > (1u << 26)) asm volatile("trap;");
+    }
+}
+
 // x^-0.75 for the LRN (x >= 1): rsqrt(x) * sqrt(rsqrt(x)); ~3 ulp, against powf's ~20 instructions
 __device__ __forceinline__ float pow_m075(float x) {
     const float r = rsqrtf(x);
@@ -221,6 +238,13 @@ __device__ __forceinline__ void umma_f16_pair(uint32_t tmem_d, uint64_t desc_a, 
         "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
         :
         : "r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit_pair_addr(uint32_t bar_addr) {
+    asm volatile(
+        "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+        :
+        : "r"(bar_addr), "h"((unsigned short)3)
         : "memory");
 }
 // arrive (once) on the barrier at this offset in BOTH CTAs when the pair's prior MMAs completed

@@ -182,35 +182,48 @@ conv_tc2_kernel(const __grid_constant__ GemmLayer L) {
             uint32_t slot_phase = 0, phase = 0, acc_phase = 0;
             long long c_wait_op = 0, c_wait_tm = 0, c_kb = 0, c_start = 0, t0 = 0;
             if (DBG) c_start = clock64();
+            // The time this warp spends between two k-blocks is on the critical path of the N = 128
+            // layers (12 MMAs of 64 clk each per k-block), so everything loop-invariant lives in
+            // registers: barrier addresses, the weight ring's descriptor base, the slab plane offset.
+            // (through an opaque move: otherwise the compiler re-derives each address where it is
+            // used, S2R SR_CgaCtaId included, instead of keeping it)
+            auto keep = [](uint32_t v) { uint32_t r; asm volatile("mov.u32 %0, %1;" : "=r"(r) : "r"(v)); return r; };
+            const uint32_t adr_full_b = keep(smem_u32(&full_b[0])), adr_empty_b = keep(smem_u32(&empty_b[0]));
+            const uint32_t adr_full_s = keep(smem_u32(&full_s[0])), adr_empty_s = keep(smem_u32(&empty_s[0]));
+            const uint32_t adr_tm_full = keep(smem_u32(&tmem_full_bar[0])), adr_tm_empty = keep(smem_u32(&tmem_empty_bar[0]));
+            const uint32_t b_ring_lo = keep(desc_lo(smem_u32(smem_b)));
+            const uint32_t slab_ring_lo = keep(desc_lo(smem_u32(smem)));
+            const uint32_t slab_slot_lo = (uint32_t)(slab_slot_bytes >> 4);
+            const uint32_t b_stage_lo = (uint32_t)(b_stage_bytes >> 4);
+            const uint32_t a_lo_plane = (uint32_t)(slab_plane >> 4);
+            const int off_min8 = L.off_min * 8;
             for (int tile = pair_id; tile < total_tiles; tile += num_pairs) {
                 int in_chunk = 0, kb = 0;
                 for (int cb = 0; cb < L.cblocks; ++cb) {
                     if (DBG) t0 = clock64();
-                    mbar_wait(&full_s[slot], slot_phase);
+                    mbar_wait_addr(adr_full_s + 8u * (uint32_t)slot, slot_phase);
                     if (DBG) c_wait_op += clock64() - t0;
-                    const uint32_t slab_lo = desc_lo(smem_u32(smem + slot * slab_slot_bytes));
+                    const uint32_t slab_lo = slab_ring_lo + (uint32_t)slot * slab_slot_lo - (uint32_t)off_min8;
+                    const int nk = (cb + 1 == L.cblocks) ? L.last_ksteps : BLOCK_K / UMMA_K;
                     for (int t = 0; t < L.taps; ++t) {
                         if (in_chunk == 0) {
                             if (DBG) t0 = clock64();
-                            mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1u);
+                            mbar_wait_addr(adr_tm_empty + 8u * (uint32_t)acc, acc_phase ^ 1u);
                             if (DBG) c_wait_tm += clock64() - t0;
                         }
+                        const uint32_t a_hi32 = slab_lo + (uint32_t)(L.row_off[t] * 8);
+                        const uint32_t a_lo32 = a_hi32 + a_lo_plane;
+                        const uint32_t b_hi32 = b_ring_lo + (uint32_t)stage * b_stage_lo;
+                        const uint32_t b_lo32 = b_hi32 + (uint32_t)(B_PLANE_BYTES >> 4);
+                        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * ACC_STRIDE);
                         if (DBG) t0 = clock64();
-                        mbar_wait(&full_b[stage], phase);
+                        mbar_wait_addr(adr_full_b + 8u * (uint32_t)stage, phase);
                         if (DBG) { c_wait_op += clock64() - t0; ++c_kb; }
                         tc_fence_after();
                         ++kb;
                         const bool chunk_end = (in_chunk + 1 == chunk) || (kb == kblocks);
                         if (elect_one()) {
-                            const uint32_t tmem_d = tmem_base + (uint32_t)(acc * ACC_STRIDE);
-                            const uint32_t a_hi32 = slab_lo + (uint32_t)((L.row_off[t] - L.off_min) * 8);
-                            const uint32_t a_lo32 = a_hi32 + (uint32_t)(slab_plane >> 4);
-                            const uint32_t b_hi32 = desc_lo(smem_u32(smem_b + stage * b_stage_bytes));
-                            const uint32_t b_lo32 = b_hi32 + (uint32_t)(B_PLANE_BYTES >> 4);
-                            const int nk = (cb + 1 == L.cblocks) ? L.last_ksteps : BLOCK_K / UMMA_K;
-#pragma unroll
-                            for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-                                if (k >= nk) break;
+                            auto kstep = [&](int k) {
                                 const uint32_t ko = (uint32_t)(k * UMMA_K * 2 / 16);
                                 const uint32_t accum = (in_chunk > 0 || k > 0) ? 1u : 0u;
                                 umma_f16_pair(tmem_d, make_desc(a_hi32 + ko), make_desc(b_hi32 + ko), idesc, accum);
@@ -218,10 +231,17 @@ conv_tc2_kernel(const __grid_constant__ GemmLayer L) {
                                     umma_f16_pair(tmem_d, make_desc(a_hi32 + ko), make_desc(b_lo32 + ko), idesc, 1u);
                                 if (A_LO)
                                     umma_f16_pair(tmem_d, make_desc(a_lo32 + ko), make_desc(b_hi32 + ko), idesc, 1u);
+                            };
+                            // straight-line code for the common full block: no per-k-step test
+                            kstep(0);
+                            if (nk == BLOCK_K / UMMA_K) {
+                                kstep(1); kstep(2); kstep(3);
+                            } else {
+                                for (int k = 1; k < nk; ++k) kstep(k);
                             }
-                            umma_commit_pair(&empty_b[stage]);
-                            if (t + 1 == L.taps) umma_commit_pair(&empty_s[slot]);
-                            if (chunk_end) umma_commit_pair(&tmem_full_bar[acc]);
+                            umma_commit_pair_addr(adr_empty_b + 8u * (uint32_t)stage);
+                            if (t + 1 == L.taps) umma_commit_pair_addr(adr_empty_s + 8u * (uint32_t)slot);
+                            if (chunk_end) umma_commit_pair_addr(adr_tm_full + 8u * (uint32_t)acc);
                         }
                         __syncwarp();
                         if (++stage == L.n_b_stages) { stage = 0; phase ^= 1u; }
