@@ -45,7 +45,7 @@ constexpr int MAX_B_STAGES = 8;
 // 128 B payload + 16 B pad (whole 128-byte lines per store); STG = 16: 64 B + 16 B (half the
 // shared memory, chosen where it buys the weight ring a 4th stage)
 constexpr int SMEM_TOTAL = 222 * 1024;
-__host__ __device__ constexpr int stage_row_bytes(int stg) { return stg == 32 ? 144 : 80; }
+__host__ __device__ constexpr int stage_row_bytes(int stg) { return stg == 32 ? 144 : (stg == 16 ? 80 : 48); }
 __host__ __device__ constexpr int stage_bytes(int stg) { return 8 * 32 * stage_row_bytes(stg); }
 __host__ __device__ constexpr int operand_budget(int stg) { return SMEM_TOTAL - stage_bytes(stg); }
 constexpr int TMEM_COLS = 512;
@@ -382,6 +382,52 @@ conv_tc2_kernel(const __grid_constant__ GemmLayer L) {
                     __syncwarp();
                 }
             }
+            } else if constexpr (STG == 8) {
+            // 8 columns per pass (32 B payload + 16 B pad per row): the smallest staging tile, chosen where
+            // it buys the weight ring a 5th stage (conv2: two 63.5 KB slab slots leave 75-83 KB)
+#pragma unroll
+            for (int c = 0; c < COLS_PER_THREAD / 8; ++c) {
+                float v[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    float x = sum[c * 8 + j] + bias_s[col0 + c * 8 + j];
+                    v[j] = L.relu ? fmaxf(x, 0.f) : x;
+                }
+                const long long gcol = n0 + col0 + c * 8;
+                uint4* my = reinterpret_cast<uint4*>(stg + lane * STAGE_ROW_BYTES);
+                if (L.out_f32) {
+                    my[0] = make_uint4(__float_as_uint(v[0]), __float_as_uint(v[1]), __float_as_uint(v[2]), __float_as_uint(v[3]));
+                    my[1] = make_uint4(__float_as_uint(v[4]), __float_as_uint(v[5]), __float_as_uint(v[6]), __float_as_uint(v[7]));
+                    __syncwarp();
+                    // 2 lanes cover one row's 32 B; one instruction writes 16 rows x 1 whole sector
+#pragma unroll
+                    for (int it = 0; it < 2; ++it) {
+                        const int r = it * 16 + (lane >> 1), ch = lane & 1;
+                        if ((row_mask >> r) & 1u) {
+                            const uint4 val = *reinterpret_cast<const uint4*>(stg + r * STAGE_ROW_BYTES + ch * 16);
+                            *reinterpret_cast<uint4*>(L.out_f32 + (row0 + r) * (long long)L.ldc + gcol + ch * 4) = val;
+                        }
+                    }
+                    __syncwarp();
+                }
+                if (L.out_hi) {                                  // one 16-byte store per row and plane
+                    uint32_t ph[4], pl[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const __half h0 = __float2half_rn(v[2 * j]);
+                        const __half h1 = __float2half_rn(v[2 * j + 1]);
+                        const __half l0 = __float2half_rn(v[2 * j] - __half2float(h0));
+                        const __half l1 = __float2half_rn(v[2 * j + 1] - __half2float(h1));
+                        ph[j] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
+                        pl[j] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
+                    }
+                    if ((row_mask >> lane) & 1u) {
+                        const long long o = (row0 + lane) * (long long)L.ldc + gcol;
+                        *reinterpret_cast<uint4*>(L.out_hi + o) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+                        *reinterpret_cast<uint4*>(L.out_lo + o) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+                    }
+                }
+            }
             } else {
 #pragma unroll
             for (int c = 0; c < COLS_PER_THREAD / 16; ++c) {
@@ -509,6 +555,9 @@ int launch_passes_stg(const GemmLayer& L, int num_sms, cudaStream_t stream) {
 
 template <int BLOCK_N>
 int launch_passes(const GemmLayer& L, int num_sms, cudaStream_t stream) {
+    if constexpr (BLOCK_N == 128) {
+        if (L.stage_cols == 8) return launch_passes_stg<BLOCK_N, 8>(L, num_sms, stream);
+    }
     return L.stage_cols == 16 ? launch_passes_stg<BLOCK_N, 16>(L, num_sms, stream)
                               : launch_passes_stg<BLOCK_N, 32>(L, num_sms, stream);
 }
@@ -535,6 +584,9 @@ int plan_slab_pair(GemmLayer& L) {
     if (nb < 4) {
         const int nb16 = (operand_budget(16) - L.n_slab_slots * slot) / stage;
         if (nb16 > nb) { nb = nb16; L.stage_cols = 16; }
+        // the 8-column tile only where it buys yet another stage (128-column tiles only)
+        const int nb8 = (operand_budget(8) - L.n_slab_slots * slot) / stage;
+        if (L.block_n == 128 && nb8 > nb && L.allow_stg8) { nb = nb8; L.stage_cols = 8; }
     }
     if (nb > MAX_B_STAGES) nb = MAX_B_STAGES;
     if (nb < 2) return fail(-1, "conv2: shared memory budget too small for this layer");

@@ -71,6 +71,7 @@ struct GemmLayer {
     int off_min;               // min(row_off)
     int n_slab_slots, n_b_stages;
     int acc_bufs;              // pair kernel: TMEM accumulator buffers (2, or 4 when block_n <= 128)
+    int allow_stg8;            // pair kernel: plan_slab_pair may choose the 8-column staging tile
     int stage_cols;            // pair kernel: epilogue staging width (32, or 16 to free smem for weight stages)
     int desc_base_offset_mode; // 1: descriptor base_offset = (addr >> 7) & 7 for shifted starts
     // optional cycle counters (development): 8 x unsigned long long, atomically accumulated per CTA

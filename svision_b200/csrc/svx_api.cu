@@ -286,6 +286,7 @@ int setup_layer(svx_handle* h, int li, const __half* a_hi, const __half* a_lo, l
     int a_box_rows = GEMM_BLOCK_M, b_box_rows = s.block_n;
     if (h->use_slab && h->use_pair && s.block_n_pair > 0) {
         L.block_n = s.block_n_pair;
+        { const char* e = std::getenv("SVX_STG8"); L.allow_stg8 = e ? std::atoi(e) : 1; }   // SVX_STG8=0: A/B
         if ((rc = plan_slab_pair(L))) return rc;
         if (const char* e = std::getenv("SVX_ACC")) L.acc_bufs = std::atoi(e);   // development A/B
         L.desc_base_offset_mode = h->desc_bo_mode;
