@@ -397,8 +397,9 @@ def run_gpu(args):
                          "note": "the 3-pass fp16-split parity recipe executes 3x the algorithmic FLOPs and the "
                                  "padded grids another 1.15x (29^2/27^2, 14^2/13^2): frac counts algorithmic "
                                  "FLOPs only, so 1/3.46 = 0.29 of a same-clock peak is the ceiling by "
-                                 "construction (per-k-block cycle counters: the MMA pipe is 90-98 % busy, "
-                                 "profiles/README.md); conv1 (0.211 GFLOP/site) runs in the fused front end"},
+                                 "construction, 0.33 for the layers with less padding (per-k-block cycle counters: "
+                                 "the layers run at 94-99.7 % of their MMA-bound time, profiles/README.md); "
+                                 "conv1 (0.211 GFLOP/site) runs in the fused front end"},
             "encoder_roofline": None if enc is None else {
                 "kernel": "encode_kernel<fp16 NHWC> (svx_encode: rows -> 227x227x3 16-bit images in HBM)",
                 "bound": "hbm", "achieved": ENC_BYTES_PER_SITE * enc[1] / (enc[0] * 1e-3) / 1e9,
