@@ -78,7 +78,8 @@ typedef struct svx_handle svx_handle;
 
 /* Replaces Predict.run's model setup (src/network/predict.py:155-189: graph build +
  * Saver.restore).  `weights` may be NULL for an encoder-only handle.  `max_batch` is the
- * micro-batch (sites resident on the device at once; workspaces are sized for it). */
+ * micro-batch (sites resident on the device at once; workspaces are sized for it: ~1.4 MB of HBM per
+ * site, 1..65536).  The buffers of the dense conv1 path are allocated by the first svx_forward. */
 int svx_create(const svx_weights *weights, int device, int64_t max_batch, int precision,
                svx_handle **out);
 void svx_destroy(svx_handle *h);
@@ -90,13 +91,15 @@ int svx_encode(svx_handle *h, const int32_t *rows_dev, int64_t n, void *images_d
                void *stream);
 
 /* Replaces sess.run(score) (predict.py:209 -> alexnet.py:26-58) on caller-provided images:
- * images_dev NHWC [n][227][227][3] of `dtype` -> logits_dev float32[n][5]. */
+ * images_dev NHWC [n][227][227][3] of `dtype` -> logits_dev float32[n][5].  Arbitrary images take
+ * the dense tcgen05 conv1 (1024 sites per pass); the classify entries below use the fused sparse
+ * front end instead, which is exact only for images this library's encoder produces. */
 int svx_forward(svx_handle *h, const void *images_dev, int dtype, int64_t n, float *logits_dev,
                 void *stream);
 
 /* The fused hot path on device buffers: rows_dev -> labels_dev int32[n] (argmax, predict.py:209),
  * probs_dev float32[n][5] (softmax), logits_dev float32[n][5] (may be NULL).  Images never
- * leave the device and are written once, in the conv1 operand layout.  Asynchronous. */
+ * leave the device: the first tensor that reaches HBM is the conv2 operand.  Asynchronous. */
 int svx_classify_device(svx_handle *h, const int32_t *rows_dev, int64_t n, int32_t *labels_dev,
                         float *probs_dev, float *logits_dev, void *stream);
 
@@ -116,6 +119,24 @@ typedef struct {
 int svx_classify_device_calls(svx_handle *h, const int32_t *rows_dev, int64_t n, svx_call *calls_dev,
                               void *stream);
 
+/* ---- several GPUs behind one handle, in ONE process -----------------------------------------------
+ * The reference drives Step 2 from a single `SVision` process (SVision:296-341).  svx_multi gives
+ * that caller every GPU of the box without torchrun: one svx_handle and one host thread per device;
+ * the rows of a call are cut into chunks which the devices take from a shared counter (a slower GPU
+ * takes fewer), each result is written straight to its place in the caller's arrays (file order is
+ * preserved, no gather).  Same results as svx_classify, bit for bit: sites are independent.
+ *   devices[ndev]   CUDA device ordinals, distinct
+ *   max_batch       micro-batch per device (as svx_create)
+ * svx_multi_last_split reports how many sites each device processed in the last call. */
+typedef struct svx_multi svx_multi;
+int svx_multi_create(const svx_weights *weights, const int *devices, int ndev, int64_t max_batch,
+                     int precision, svx_multi **out);
+int svx_multi_classify(svx_multi *m, const int32_t *rows_host, int64_t n, int32_t *labels_host,
+                       float *probs_host);
+int svx_multi_device_count(const svx_multi *m);
+int svx_multi_last_split(const svx_multi *m, int64_t *sites_per_device /* [ndev] */);
+void svx_multi_destroy(svx_multi *m);
+
 /* ---- multi-GPU result exchange ---------------------------------------------------
  * The reference parallelises Step 2 with one process per chromosome and temp files
  * (SVision:311-323); here sites shard contiguously over one process per GPU, and the only exchange
@@ -129,8 +150,11 @@ int svx_classify_device_calls(svx_handle *h, const int32_t *rows_dev, int64_t n,
  *                 the next-but-one svx_classify_exchange (two buffers alternate).  Consume it on
  *                 `stream` (or after synchronising) before calling again.
  * All ranks must call svx_classify_exchange the same number of times.  A rank that does not show up
- * within SVX_EXCHANGE_TIMEOUT_MS (default 5000) is reported by svx_exchange_status, which
- * synchronises the device; the wait never hangs the GPU. */
+ * within SVX_EXCHANGE_TIMEOUT_MS (default 30000; covers start skew such as one rank still parsing its
+ * BED) cannot hang the GPU: the wait kernel gives up, POISONS that rank's calls in the local gathered
+ * buffer (label -1, score NaN -- stale results of an earlier epoch can not be mistaken for this one's)
+ * and raises a sticky error word in mapped host memory.  The error is returned by svx_exchange_status
+ * (which synchronises the device and clears it) and by every later svx_classify_exchange until then. */
 #define SVX_IPC_HANDLE_BYTES 64
 typedef struct svx_exchange svx_exchange;
 int svx_exchange_create(svx_handle *h, int rank, int world, int64_t sites_per_rank, svx_exchange **out);
@@ -143,25 +167,26 @@ void svx_exchange_destroy(svx_exchange *x);
 
 /* Parity/debug: copy the activation named `name` of the LAST micro-batch (first `n` sites) to
  * host as float32, NHWC, valid positions only.  Names: "conv1" [55][55][96], "norm1"
- * [27][27][96], "conv2" [27][27][256], "norm2" [13][13][256], "conv3"/"conv4" [13][13][384],
- * "conv5" [13][13][256], "pool5" [6][6][256], "fc6"/"fc7" [4096]. */
+ * [27][27][96], "norm2" [13][13][256], "conv3"/"conv4" [13][13][384], "pool5" [6][6][256],
+ * "fc6"/"fc7" [4096].  ("conv1" exists only after svx_forward; the full-resolution outputs of conv2 and
+ * conv5 are never materialised: their max-pool runs in the layer's epilogue.) */
 int svx_debug_activation(svx_handle *h, const char *name, int64_t n, float *out_host);
 
 /* Standalone tcgen05 GEMM self-test entry (used by tests): C[M][N] = A[M][K] * B[N][K]^T with
- * fp16 hi/lo operands given as float32 on the device; returns float32 C on the device. */
+ * fp16 hi/lo operands given as float32 on the device; returns float32 C on the device.  block_n is
+ * the tile width of the layer kernel: 96, 128, 192 or 256. */
 int svx_gemm_selftest(int device, const float *a_dev, const float *b_dev, float *c_dev,
                       int64_t m, int64_t n, int64_t k, int block_n, int precision, void *stream);
 
 /* Shifted-GEMM self-test: C[m][n] = sum_t sum_c A[m + row_off[t]][c] * B[n][t*k_per_tap + c]
- * (rows outside A read as zero).  flags bit0: slab kernel (conv_tc.cu) instead of the per-tap
- * kernel (gemm_tc.cu); bit1: descriptor base_offset mode for row-shifted slab views; bit2: CTA-pair
- * kernel (conv_tc2.cu, cta_group::2; block_n 128/192/256). */
+ * (rows outside A read as zero), through the same layer kernel (layer_tc.cu). */
 int svx_conv_selftest(int device, const float *a_dev, const float *b_dev, float *c_dev, int64_t m,
                       int64_t n, int64_t k_per_tap, int taps, const int *row_off, int block_n,
-                      int precision, int flags, void *stream);
+                      int precision, void *stream);
 
 /* Development aid: per-role cycle counters of the 7 tensor-core layers, uint64 out[7][8]
- * (handle created with SVX_DBG=1 in the environment): 0 MMA-role total, 1 MMA wait operands,
+ * (handle created with SVX_DBG=1 in the environment -- besides SVX_EXCHANGE_TIMEOUT_MS the only
+ * environment variable the library reads): 0 MMA-role total, 1 MMA wait operands,
  * 2 MMA wait TMEM-empty, 3 k-blocks, 4 producer wait smem-empty, 5 epilogue wait TMEM-full,
  * 6 epilogue drain, 7 epilogue store; summed over CTAs. */
 int svx_debug_counters(svx_handle *h, uint64_t *out, int reset);
@@ -170,7 +195,9 @@ int svx_debug_counters(svx_handle *h, uint64_t *out, int reset);
  * roofline numbers).  Slots: 0 encode, 1 conv1, 2 pool1+lrn1, 3 conv2, 4 pool2+lrn2, 5 conv3,
  * 6 conv4, 7 conv5, 8 pool5, 9 fc6, 10 fc7, 11 fc8+softmax.  svx_profile_read synchronises,
  * adds the elapsed milliseconds and launch counts since the last reset into ms_out[12] /
- * launches_out[12] (either may be NULL) and optionally resets. */
+ * launches_out[12] (either may be NULL) and optionally resets.  Slot 3 includes pool2 and slot 7
+ * pool5 (fused into the layer's epilogue); slots 4 and 8 are the passes that finish them (LRN2 +
+ * fp16 split; fp16 split). */
 #define SVX_PROFILE_SLOTS 12
 int svx_set_profiling(svx_handle *h, int enable);
 int svx_profile_read(svx_handle *h, float *ms_out, int64_t *launches_out, int reset);

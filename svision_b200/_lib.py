@@ -21,6 +21,8 @@ SYMBOLS = (
     "svx_classify_device_calls", "svx_exchange_create", "svx_exchange_export", "svx_exchange_attach",
     "svx_classify_exchange", "svx_exchange_status", "svx_exchange_destroy",
     "svx_calls_aggregate", "svx_np_mean_f32", "svx_np_std_i64",
+    "svx_multi_create", "svx_multi_classify", "svx_multi_device_count", "svx_multi_last_split",
+    "svx_multi_destroy",
 )
 IPC_HANDLE_BYTES = 64
 
@@ -63,7 +65,7 @@ def load() -> ctypes.CDLL:
     lib.svx_debug_activation.restype = i32
     lib.svx_gemm_selftest.argtypes = [i32, vp, vp, vp, i64, i64, i64, i32, i32, vp]
     lib.svx_gemm_selftest.restype = i32
-    lib.svx_conv_selftest.argtypes = [i32, vp, vp, vp, i64, i64, i64, i32, vp, i32, i32, i32, vp]
+    lib.svx_conv_selftest.argtypes = [i32, vp, vp, vp, i64, i64, i64, i32, vp, i32, i32, vp]
     lib.svx_conv_selftest.restype = i32
     lib.svx_debug_counters.argtypes = [vp, vp, i32]
     lib.svx_debug_counters.restype = i32
@@ -102,6 +104,17 @@ def load() -> ctypes.CDLL:
     lib.svx_np_mean_f32.restype = i32
     lib.svx_np_std_i64.argtypes = [vp, i64, vp]
     lib.svx_np_std_i64.restype = i32
+    lib.svx_multi_create.argtypes = [ctypes.POINTER(SvxWeights), ctypes.POINTER(i32), i32, i64, i32,
+                                     ctypes.POINTER(vp)]
+    lib.svx_multi_create.restype = i32
+    lib.svx_multi_classify.argtypes = [vp, vp, i64, vp, vp]
+    lib.svx_multi_classify.restype = i32
+    lib.svx_multi_device_count.argtypes = [vp]
+    lib.svx_multi_device_count.restype = i32
+    lib.svx_multi_last_split.argtypes = [vp, vp]
+    lib.svx_multi_last_split.restype = i32
+    lib.svx_multi_destroy.argtypes = [vp]
+    lib.svx_multi_destroy.restype = None
     lib.svx_max_batch.argtypes = [vp]
     lib.svx_max_batch.restype = i64
     lib.svx_device.argtypes = [vp]

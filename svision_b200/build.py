@@ -14,7 +14,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libsvx.so")
-SOURCES = ["encoder.cu", "front.cu", "gemm_tc.cu", "conv_tc.cu", "conv_tc2.cu", "cnn_aux.cu", "svx_api.cu",
+SOURCES = ["encoder.cu", "front.cu", "layer_tc.cu", "cnn_aux.cu", "svx_api.cu", "svx_multi.cpp",
            "host_bed.cpp", "host_pairs.cpp", "host_calls.cpp"]
 HEADERS = ["common.cuh", "kernels.h", "encoder_bitmap.cuh", os.path.join("..", "..", "include", "svx.h")]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]

@@ -186,18 +186,89 @@ class Classifier:
         return out
 
     def debug_activation(self, name: str, n: int) -> np.ndarray:
-        shapes = {"conv1": (55, 55, 96), "norm1": (27, 27, 96), "conv2": (27, 27, 256),
-                  "norm2": (13, 13, 256), "conv3": (13, 13, 384), "conv4": (13, 13, 384),
-                  "conv5": (13, 13, 256), "pool5": (6, 6, 256), "fc6": (4096,), "fc7": (4096,)}
+        # (conv2 / conv5 at full resolution never exist: their max-pool runs in the layer's epilogue)
+        shapes = {"conv1": (55, 55, 96), "norm1": (27, 27, 96), "norm2": (13, 13, 256),
+                  "conv3": (13, 13, 384), "conv4": (13, 13, 384), "pool5": (6, 6, 256),
+                  "fc6": (4096,), "fc7": (4096,)}
         out = np.empty((n,) + shapes[name], dtype=np.float32)
         _lib.check(self._lib.svx_debug_activation(self._h, name.encode(), n, out.ctypes.data),
                    "svx_debug_activation")
         return out
 
 
+class MultiClassifier:
+    """Every GPU of the box behind one object, in ONE process (C-ABI ``svx_multi_*``): what the
+    reference's single ``SVision`` process (``SVision:296-341``) would hold.  ``classify`` has the
+    contract of ``Classifier.classify`` and returns the same bits; the rows of a call are spread
+    over the devices in chunks taken from a shared counter, so a slower GPU takes fewer."""
+
+    def __init__(self, model, devices=None, max_batch: int = 8192, precision: str = "3pass"):
+        if not torch.cuda.is_available():
+            raise _lib.SvxError("no CUDA device: the encode+classify path has no CPU fallback")
+        self._lib = _lib.load()
+        if devices is None:
+            devices = list(range(torch.cuda.device_count()))
+        self.devices = [int(d) for d in devices]
+        self.max_batch = int(max_batch)
+        prec = {"3pass": _lib.PRECISION_3PASS, "1pass": _lib.PRECISION_1PASS}[precision]
+        if isinstance(model, str):
+            model = _weights.load_checkpoint(model)
+        _weights.check_weights(model)
+        w = _lib.SvxWeights()
+        keep = []
+        for layer in _weights.WEIGHT_SHAPES:
+            for kind, short in (("weights", "w"), ("biases", "b")):
+                a = np.ascontiguousarray(model[f"{layer}/{kind}"], dtype=np.float32)
+                keep.append(a)
+                setattr(w, f"{layer}_{short}", a.ctypes.data)
+        dev = (ctypes.c_int * len(self.devices))(*self.devices)
+        h = ctypes.c_void_p()
+        _lib.check(self._lib.svx_multi_create(ctypes.byref(w), dev, len(self.devices), self.max_batch,
+                                              prec, ctypes.byref(h)), "svx_multi_create")
+        self._h = h
+        self.has_model = True
+        del keep
+
+    def close(self) -> None:
+        if getattr(self, "_h", None):
+            self._lib.svx_multi_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def classify(self, rows, labels_out: Optional[np.ndarray] = None,
+                 probs_out: Optional[np.ndarray] = None):
+        rows = _as_rows(rows)
+        n = rows.shape[0]
+        labels = labels_out if labels_out is not None else np.empty((n,), dtype=np.int32)
+        probs = probs_out if probs_out is not None else np.empty((n, NUM_CLASSES), dtype=np.float32)
+        assert labels.dtype == np.int32 and probs.dtype == np.float32
+        assert labels.flags.c_contiguous and probs.flags.c_contiguous
+        _lib.check(self._lib.svx_multi_classify(self._h, rows.ctypes.data, n, labels.ctypes.data,
+                                                probs.ctypes.data), "svx_multi_classify")
+        return labels, probs
+
+    def last_split(self) -> list:
+        """Sites each device processed in the last ``classify`` call."""
+        out = np.zeros(len(self.devices), dtype=np.int64)
+        _lib.check(self._lib.svx_multi_last_split(self._h, out.ctypes.data), "svx_multi_last_split")
+        return out.tolist()
+
+
 def gemm_selftest(a: torch.Tensor, b: torch.Tensor, block_n: int = 128,
                   precision: str = "3pass") -> torch.Tensor:
-    """C = A @ B.T through the tcgen05 layer kernel (A [M,K], B [N,K] float32 cuda tensors)."""
+    """C = A @ B.T through the tcgen05 layer kernel (A [M,K], B [N,K] float32 cuda tensors;
+    block_n 96 / 128 / 192 / 256, N a multiple of it)."""
     lib = _lib.load()
     assert a.is_cuda and b.is_cuda and a.dtype == torch.float32 and b.dtype == torch.float32
     a, b = a.contiguous(), b.contiguous()
@@ -213,9 +284,8 @@ def gemm_selftest(a: torch.Tensor, b: torch.Tensor, block_n: int = 128,
 
 
 def conv_selftest(a: torch.Tensor, b: torch.Tensor, row_off, block_n: int = 128,
-                  precision: str = "3pass", slab: bool = True, base_offset_mode: int = 0,
-                  pair: bool = False) -> torch.Tensor:
-    """C[m,n] = sum_t A[m + row_off[t], :] @ B[n, t*K:(t+1)*K].T through a tensor-core layer kernel
+                  precision: str = "3pass") -> torch.Tensor:
+    """C[m,n] = sum_t A[m + row_off[t], :] @ B[n, t*K:(t+1)*K].T through the tensor-core layer kernel
     (A [M,K], B [N,taps*K] float32 cuda tensors; rows outside A read as zero)."""
     lib = _lib.load()
     a, b = a.contiguous(), b.contiguous()
@@ -225,9 +295,8 @@ def conv_selftest(a: torch.Tensor, b: torch.Tensor, row_off, block_n: int = 128,
     assert b.shape[1] == k * offs.size
     c = torch.empty((m, n), dtype=torch.float32, device=a.device)
     prec = {"3pass": _lib.PRECISION_3PASS, "1pass": _lib.PRECISION_1PASS}[precision]
-    flags = (1 if slab else 0) | ((base_offset_mode & 1) << 1) | (4 if pair else 0)
     _lib.check(lib.svx_conv_selftest(a.device.index or 0, a.data_ptr(), b.data_ptr(), c.data_ptr(),
-                                     m, n, k, int(offs.size), offs.ctypes.data, block_n, prec, flags,
+                                     m, n, k, int(offs.size), offs.ctypes.data, block_n, prec,
                                      torch.cuda.current_stream(a.device).cuda_stream),
                "svx_conv_selftest")
     return c

@@ -107,6 +107,89 @@ __global__ void __launch_bounds__(256) pool_kernel(const PoolParams p, long long
     }
 }
 
+// Second half of the pool fused into the conv2 / conv5 epilogues (layer_tc.cu, STG = 0): one warp per
+// pooled position, lane = 8 consecutive channels of 256.  Reads the window maximum (two parts where the
+// window straddles a 128-row chunk of the conv's rows), applies the LRN (conv2) and writes the fp16
+// hi/lo planes of the next layer's operand.  HBM bound: 1-2 KB read + 1 KB written per position.
+template <bool LRN>
+__global__ void __launch_bounds__(256) finish_pooled_kernel(const FinishParams p, long long total_pos) {
+    constexpr int U = 4;                                  // positions per warp and pass: 4 KB of loads in flight
+    const int lane = threadIdx.x & 31;
+    const int warps_per_block = blockDim.x >> 5;
+    const long long warp0 = (long long)blockIdx.x * warps_per_block + (threadIdx.x >> 5);
+    const long long nwarps = (long long)gridDim.x * warps_per_block;
+    const int per_img = p.pool_h * p.pool_w;
+    for (long long pos0 = warp0 * U; pos0 < total_pos; pos0 += nwarps * U) {
+        float4 va[U], vb[U], wa[U], wb[U];
+        long long img_u[U];
+        int y_u[U], x_u[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const long long pos = pos0 + u;
+            wa[u] = wb[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (pos < total_pos) {
+                img_u[u] = pos / per_img;
+                const int rem = (int)(pos - img_u[u] * per_img);
+                y_u[u] = rem / p.pool_w;
+                x_u[u] = rem - y_u[u] * p.pool_w;
+                const float4* src = reinterpret_cast<const float4*>(p.pooled + pos * 256 + lane * 8);
+                va[u] = __ldcs(src);
+                vb[u] = __ldcs(src + 1);
+                if (pool_crosses(img_u[u], y_u[u], x_u[u], p.in_pos_per_img, p.in_grid_w)) {
+                    const float4* src2 = reinterpret_cast<const float4*>(p.pooled2 + pos * 256 + lane * 8);
+                    wa[u] = __ldcs(src2);
+                    wb[u] = __ldcs(src2 + 1);
+                }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const long long pos = pos0 + u;
+            if (pos >= total_pos) break;                  // warp-uniform
+            const long long img = img_u[u];
+            const int y = y_u[u], x = x_u[u];
+            // values are >= 0 (post-ReLU), and a missing second part reads as 0
+            const float m[8] = {fmaxf(va[u].x, wa[u].x), fmaxf(va[u].y, wa[u].y), fmaxf(va[u].z, wa[u].z),
+                                fmaxf(va[u].w, wa[u].w), fmaxf(vb[u].x, wb[u].x), fmaxf(vb[u].y, wb[u].y),
+                                fmaxf(vb[u].z, wb[u].z), fmaxf(vb[u].w, wb[u].w)};
+            float out[8];
+            if (LRN) {
+                float sq[12];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) sq[j + 2] = m[j] * m[j];
+                const float l0 = __shfl_up_sync(0xffffffffu, sq[8], 1);        // lane-1's channel 6
+                const float l1 = __shfl_up_sync(0xffffffffu, sq[9], 1);        // lane-1's channel 7
+                const float r0 = __shfl_down_sync(0xffffffffu, sq[2], 1);      // lane+1's channel 0
+                const float r1 = __shfl_down_sync(0xffffffffu, sq[3], 1);      // lane+1's channel 1
+                sq[0] = lane > 0 ? l0 : 0.f;
+                sq[1] = lane > 0 ? l1 : 0.f;
+                sq[10] = lane < 31 ? r0 : 0.f;
+                sq[11] = lane < 31 ? r1 : 0.f;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float s5 = sq[j] + sq[j + 1] + sq[j + 2] + sq[j + 3] + sq[j + 4];
+                    out[j] = m[j] * pow_m075(1.0f + 2e-5f * s5);
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) out[j] = m[j];
+            }
+            const long long o = (img * p.out_pos_per_img + (long long)y * p.out_grid_w + x) * p.out_ld + lane * 8;
+            uint32_t ph[4], pl[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const __half h0 = __float2half_rn(out[2 * j]), h1 = __float2half_rn(out[2 * j + 1]);
+                const __half e0 = __float2half_rn(out[2 * j] - __half2float(h0));
+                const __half e1 = __float2half_rn(out[2 * j + 1] - __half2float(h1));
+                ph[j] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
+                pl[j] = (uint32_t)__half_as_ushort(e0) | ((uint32_t)__half_as_ushort(e1) << 16);
+            }
+            *reinterpret_cast<uint4*>(p.out_hi + o) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+            *reinterpret_cast<uint4*>(p.out_lo + o) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+        }
+    }
+}
+
 // One warp per site, 8 sites per CTA.  Besides labels / probs / logits the kernel can emit the
 // 8-byte (label, score) call of every site -- what src/network/predict.py:230,251 consumes -- into
 // up to CALL_MAX_SINKS destinations: the local buffer and, in a multi-GPU exchange, the gathered
@@ -187,20 +270,35 @@ fc8_softmax_kernel(const __half* __restrict__ x_hi, const __half* __restrict__ x
 
 // One thread per rank waits until that rank's calls have landed in the local gathered buffer
 // (its fc8 kernel has published `epoch`).  Bounded: after `timeout_ns` the rank is reported in
-// *error (1 + rank) and the kernel exits instead of hanging the device.
+// *error (1 + rank), its region is poisoned and the kernel exits instead of hanging the device.
 __global__ void exchange_wait_kernel(const unsigned long long* __restrict__ my_flags, int world,
                                      unsigned long long epoch, unsigned long long timeout_ns,
-                                     unsigned int* __restrict__ error) {
+                                     unsigned int* __restrict__ error, int2* __restrict__ gathered,
+                                     long long per_rank) {
     const int r = threadIdx.x;
-    if (r >= world) return;
-    unsigned long long t0, now, v;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
-    for (;;) {
-        asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(my_flags + r) : "memory");
-        if (v >= epoch) break;
-        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
-        if (now - t0 > timeout_ns) { atomicExch(error, 1u + (unsigned)r); break; }
-        __nanosleep(200);
+    bool timed_out = false;
+    if (r < world) {
+        unsigned long long t0, now, v;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+        for (;;) {
+            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(my_flags + r) : "memory");
+            if (v >= epoch) break;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+            if (now - t0 > timeout_ns) { timed_out = true; break; }
+            __nanosleep(200);
+        }
+    }
+    unsigned int late = __ballot_sync(0xffffffffu, timed_out);
+    if (late == 0) return;
+    if (threadIdx.x == 0) {
+        *error = 1u + (unsigned)(__ffs(late) - 1);
+        __threadfence_system();
+    }
+    const int2 poison = make_int2(-1, 0x7fc00000);           // label -1, score NaN
+    while (late) {
+        const int rr = __ffs(late) - 1;
+        late &= late - 1;
+        for (long long i = threadIdx.x; i < per_rank; i += 32) gathered[(long long)rr * per_rank + i] = poison;
     }
 }
 
@@ -257,6 +355,18 @@ int launch_pool(const PoolParams& p, long long n_img, int num_sms, cudaStream_t 
     return 0;
 }
 
+int launch_finish_pooled(const FinishParams& p, long long n_img, int num_sms, cudaStream_t stream) {
+    const long long total = n_img * p.pool_h * p.pool_w;
+    if (total <= 0) return 0;
+    if (p.out_ld % 8 != 0) return fail(-1, "finish_pooled: output rows must be 16-byte aligned");
+    long long blocks = (long long)num_sms * 6;           // CTAs resident per SM at ~40 registers
+    if (blocks > (total + 31) / 32) blocks = (total + 31) / 32;
+    if (p.lrn) finish_pooled_kernel<true><<<(unsigned)blocks, 256, 0, stream>>>(p, total);
+    else       finish_pooled_kernel<false><<<(unsigned)blocks, 256, 0, stream>>>(p, total);
+    SVX_LAUNCH_CHECK("finish_pooled_kernel");
+    return 0;
+}
+
 int launch_fc8_softmax(const __half* x_hi, const __half* x_lo, const float* w8, const float* b8,
                        long long n, int32_t* labels, float* probs, float* logits,
                        const CallSinks& sinks, cudaStream_t stream) {
@@ -269,9 +379,10 @@ int launch_fc8_softmax(const __half* x_hi, const __half* x_lo, const float* w8, 
 }
 
 int launch_exchange_wait(const unsigned long long* my_flags, int world, unsigned long long epoch,
-                         unsigned long long timeout_ns, unsigned int* error, cudaStream_t stream) {
+                         unsigned long long timeout_ns, unsigned int* error, int2* gathered,
+                         long long per_rank, cudaStream_t stream) {
     if (world < 1 || world > CALL_MAX_SINKS) return fail(-1, "exchange: bad world size");
-    exchange_wait_kernel<<<1, 32, 0, stream>>>(my_flags, world, epoch, timeout_ns, error);
+    exchange_wait_kernel<<<1, 32, 0, stream>>>(my_flags, world, epoch, timeout_ns, error, gathered, per_rank);
     SVX_LAUNCH_CHECK("exchange_wait_kernel");
     return 0;
 }

@@ -1,6 +1,6 @@
 // C-ABI of libsvx (see include/svx.h): handle, one-time weight repack, HBM workspaces, the
 // per-micro-batch kernel sequence.  Host code here is plumbing; all arithmetic on the path runs in
-// the kernels of encoder.cu / gemm_tc.cu / cnn_aux.cu.
+// the kernels of encoder.cu / front.cu / layer_tc.cu / cnn_aux.cu.
 #include "../../include/svx.h"
 
 #include "common.cuh"
@@ -30,26 +30,32 @@ constexpr int P1 = S2D * S2D;                 // 3249 positions per site in x1 /
 constexpr int G2 = 29, P2 = G2 * G2;          // conv2 grid: 27 + 2 shared pad rows/cols -> 841
 constexpr int G3 = 14, P3 = G3 * G3;          // conv3-5 grid: 13 + 1 -> 196
 
-constexpr int kChunkKBlocks = 4;              // K = 256 per TMEM accumulation chain (default)
-static int chunk_kblocks() {                  // SVX_CHUNK overrides (development: precision/speed trade)
-    if (const char* e = std::getenv("SVX_CHUNK")) { const int v = std::atoi(e); if (v >= 1 && v <= 64) return v; }
-    return kChunkKBlocks;
-}
+// K = 256 per TMEM accumulation chain: the tensor core's fp32 accumulation truncates, so longer
+// chains cost precision.  conv3 / conv4 use 6: their 192-column tiles have only two
+// TMEM buffers and a per-tile store phase (~9.3k clk) longer than two 4-block chunks of MMA work, so
+// the MMA warp waited 140-170 clk per k-block for a free buffer; with K = 384 chunks it runs 13.8k clk
+// ahead: 1242 -> 1155 clk per k-block (99.7 % of the issue bound) for max |dsoftmax| 1.08e-4 -> 1.33e-4
+constexpr int kChunkKBlocks = 4;
+constexpr int kChunkKBlocksWide = 6;
+// sites per pass of the dense conv1 path (svx_forward only): its x1 / y1 buffers take 1.66 MB per
+// site and are allocated on first use
+constexpr long long kDenseBatch = 1024;
+// workspaces are ~1.4 MB per site; beyond this the request cannot fit a 180 GB device anyway
+constexpr long long kMaxBatchLimit = 65536;
 
 enum { L_CONV1 = 0, L_CONV2, L_CONV3, L_CONV4, L_CONV5, L_FC6, L_FC7, L_COUNT };
 
 struct LayerSpec {
-    int taps, cg_real, cg_pad, groups, n_total, block_n, kh, kw;
-    int block_n_pair;          // N-tile of the CTA-pair kernel (0: layer stays on the 1-CTA kernel)
+    int taps, cg_real, cg_pad, groups, n_total, block_n, kh, kw, chunk;
 };
 static const LayerSpec kSpec[L_COUNT] = {
-    /* conv1 (s2d) */ {9, 48, 64, 1, 96, 96, 3, 3, 0},
-    /* conv2       */ {25, 48, 64, 2, 256, 128, 5, 5, 128},
-    /* conv3       */ {9, 256, 256, 1, 384, 128, 3, 3, 192},
-    /* conv4       */ {9, 192, 192, 2, 384, 96, 3, 3, 192},
-    /* conv5       */ {9, 192, 192, 2, 256, 128, 3, 3, 128},
-    /* fc6         */ {1, 9216, 9216, 1, 4096, 128, 1, 1, 256},
-    /* fc7         */ {1, 4096, 4096, 1, 4096, 128, 1, 1, 256},
+    /* conv1 (s2d) */ {9, 48, 64, 1, 96, 96, 3, 3, kChunkKBlocks},
+    /* conv2       */ {25, 48, 64, 2, 256, 128, 5, 5, kChunkKBlocks},
+    /* conv3       */ {9, 256, 256, 1, 384, 192, 3, 3, kChunkKBlocksWide},
+    /* conv4       */ {9, 192, 192, 2, 384, 192, 3, 3, kChunkKBlocksWide},
+    /* conv5       */ {9, 192, 192, 2, 256, 128, 3, 3, kChunkKBlocks},
+    /* fc6         */ {1, 9216, 9216, 1, 4096, 256, 1, 1, kChunkKBlocks},
+    /* fc7         */ {1, 4096, 4096, 1, 4096, 256, 1, 1, kChunkKBlocks},
 };
 
 }  // namespace svx
@@ -62,18 +68,14 @@ struct svx_handle {
     long long max_batch = 0;
     int precision = 0;
     bool has_model = false;
-    bool use_front = true;               // fused sparse front end (front.cu) in the classify path
     float* front_w255 = nullptr;
     float* front_base = nullptr;
     float* front_scratch = nullptr;      // [front_blocks][3025][96]
     int front_blocks = 0;
-    bool use_pack = true;                // conv2 K-packing: 48-channel positions, 5 row-taps x 240 (K = 1200)
-    long long x2_group_elems = 64;       // element offset of channel group 1 in x2
-    int x2_ld = 128;                     // elements per x2 position row
-    bool use_pair = true;                // conv_tc2.cu (cta_group::2) where the layer supports it
-    bool use_slab = true;                // conv_tc.cu (A halo slab) vs gemm_tc.cu (A tile per tap)
-    int desc_bo_mode = 0;                // measured on B200: swizzle uses absolute smem address bits, so
-                                         // row-shifted slab views need base_offset 0 (mode 1 is wrong)
+    // conv2 operand, K-packed: two group planes of [B*841 + 64][48]; the 5 kw-taps of a kernel row
+    // are 240 contiguous values (5 row-taps, K = 1200)
+    long long x2_group_elems = 0;        // element offset of channel group 1 in x2
+    int x2_ld = 48;                      // elements per x2 position row
     cudaStream_t stream = nullptr;       // used by svx_classify (host entry)
     cudaEvent_t busy = nullptr;          // recorded at the end of every entry that uses the workspaces:
                                          // the next entry (possibly on another stream) waits on it
@@ -86,14 +88,16 @@ struct svx_handle {
     float* w8 = nullptr;
     float* b8 = nullptr;
 
-    __half* x1 = nullptr;                                   // [B*3249][64]
-    float* y1 = nullptr;                                    // [B*3249][96]
+    // dense conv1 path (svx_forward only), allocated on first use for kDenseBatch sites
+    long long dense_batch = 0;
+    __half* x1 = nullptr;                                   // [dense_batch*3249][64]
+    float* y1 = nullptr;                                    // [dense_batch*3249][96]
     __half *x2_hi = nullptr, *x2_lo = nullptr;              // [B*841][128]
-    float* y2 = nullptr;                                    // [B*841][256]
+    float *p2 = nullptr, *p2b = nullptr;                    // [B*169][256] pooled conv2: window maxima, two parts
     __half *x3_hi = nullptr, *x3_lo = nullptr;              // [B*196][256]
     __half *x4_hi = nullptr, *x4_lo = nullptr;              // [B*196][384]
     __half *x5_hi = nullptr, *x5_lo = nullptr;              // [B*196][384]
-    float* y5 = nullptr;                                    // [B*196][256]
+    float *p5 = nullptr, *p5b = nullptr;                    // [B*36][256] pooled conv5
     __half *x6_hi = nullptr, *x6_lo = nullptr;              // [B][9216]
     __half *x7_hi = nullptr, *x7_lo = nullptr;              // [B][4096]
     __half *x8_hi = nullptr, *x8_lo = nullptr;              // [B][4096]
@@ -126,9 +130,10 @@ struct svx_exchange {
     bool opened[CALL_MAX_SINKS] = {};
     bool attached = false;
     unsigned int* done = nullptr;                   // fc8 CTA counter
-    unsigned int* error = nullptr;                  // wait-kernel timeout report
+    unsigned int* error_host = nullptr;             // wait-kernel timeout report: mapped pinned host word,
+    unsigned int* error = nullptr;                  //   and its device alias (readable without a sync)
     unsigned long long epoch = 0;
-    unsigned long long timeout_ns = 5000000000ull;  // SVX_EXCHANGE_TIMEOUT_MS overrides
+    unsigned long long timeout_ns = 30000000000ull; // SVX_EXCHANGE_TIMEOUT_MS overrides
     size_t region_bytes() const { return (size_t)world * (size_t)per_rank * sizeof(svx_call); }
     char* region(int r, int parity) const {
         return static_cast<char*>(base[r]) + 256 + (size_t)parity * region_bytes();
@@ -174,7 +179,7 @@ constexpr int kPackLeadRows = 64;
 
 int upload_layer_weights(svx_handle* h, int li, const float* w_tf, const float* b_tf) {
     const LayerSpec& s = kSpec[li];
-    const bool packed = li == L_CONV2 && h->use_pack;
+    const bool packed = li == L_CONV2;
     const size_t K = packed ? (size_t)kPackTaps * kPackK : (size_t)s.taps * s.cg_pad;
     const size_t count = (size_t)s.n_total * K;
     std::vector<__half> hi(count), lo(count);
@@ -223,25 +228,25 @@ int upload_layer_weights(svx_handle* h, int li, const float* w_tf, const float* 
     return 0;
 }
 
-int setup_layer(svx_handle* h, int li, const __half* a_hi, const __half* a_lo, long long a_rows,
-                int lda, int grid_w, int center, float* out_f32, __half* out_hi, __half* out_lo,
-                int ldc, int pos_per_img, int valid_h, int valid_w) {
+// Geometry and epilogue of one layer.  `pool` (conv2, conv5): the layer's 3x3/2 max-pool runs in its
+// epilogue and the window maxima go to that buffer instead of a full-resolution output.
+struct LayerIO {
+    const __half* a_hi; const __half* a_lo; long long a_rows; int lda;   // operand planes [a_rows][lda]
+    int grid_w, center;                                                  // padded grid width, kernel centre
+    float* out_f32; __half* out_hi; __half* out_lo; int ldc;             // full-resolution outputs
+    int pos_per_img, valid_h, valid_w;                                   // valid-row mask (0: none)
+    float* pool; float* pool2; int pool_h, pool_w;
+};
+
+int setup_layer(svx_handle* h, int li, const LayerIO& io) {
     const LayerSpec& s = kSpec[li];
     GemmLayer& L = h->layer[li];
     std::memset(&L, 0, sizeof(L));
-    const bool packed = li == L_CONV2 && h->use_pack;
+    const bool packed = li == L_CONV2;
     const long long K = packed ? (long long)kPackTaps * kPackK : (long long)s.taps * s.cg_pad;
     int rc;
     L.block_n = s.block_n;
-    L.chunk_kblocks = chunk_kblocks();
-    if (li == L_CONV3 || li == L_CONV4) {
-        // 192-column tiles have only two TMEM buffers, and their per-tile store phase (~9.3k clk) is
-        // longer than two 4-block chunks of MMA work (9.2k clk): the MMA warp waited 140-170 clk per
-        // k-block for a free buffer.  Chunks of 6 k-blocks (K = 384) let it run 13.8k clk ahead:
-        // 1242 -> 1155 clk per k-block (99.7 % of the issue bound) for max |dsoftmax| 1.08e-4 -> 1.33e-4
-        if (!std::getenv("SVX_CHUNK")) L.chunk_kblocks = 6;
-        if (const char* e = std::getenv("SVX_CHUNK34")) { const int v = std::atoi(e); if (v >= 1 && v <= 64) L.chunk_kblocks = v; }
-    }
+    L.chunk_kblocks = s.chunk;
     L.groups = s.groups;
     L.n_per_group = s.n_total / s.groups;
     L.taps = s.taps;
@@ -251,8 +256,11 @@ int setup_layer(svx_handle* h, int li, const __half* a_hi, const __half* a_lo, l
     L.last_ksteps = GEMM_BLOCK_K / 16;
     for (int kh = 0; kh < s.kh; ++kh)
         for (int kw = 0; kw < s.kw; ++kw)
-            L.row_off[kh * s.kw + kw] = (kh - center) * grid_w + (kw - center);
-    long long a_cols = lda;                       // logical row length seen by the A tensor maps
+            L.row_off[kh * s.kw + kw] = (kh - io.center) * io.grid_w + (kw - io.center);
+    const __half* a_hi = io.a_hi;
+    const __half* a_lo = io.a_lo;
+    long long a_rows = io.a_rows;
+    long long a_cols = io.lda;                    // logical row length seen by the A tensor maps
     if (packed) {
         // one tap per kernel ROW: its 5 x 48 = 240 operand values are contiguous in the packed x2
         // (row stride 48 elements), read as 4 K-blocks through overlapping-row tensor maps; the
@@ -262,7 +270,7 @@ int setup_layer(svx_handle* h, int li, const __half* a_hi, const __half* a_lo, l
         L.last_ksteps = 3;
         L.a_group_cols = 0;
         L.a_group_rows = (int)(h->x2_group_elems / 48);
-        for (int kh = 0; kh < 5; ++kh) L.row_off[kh] = (kh - 2) * grid_w - 2;
+        for (int kh = 0; kh < 5; ++kh) L.row_off[kh] = (kh - 2) * io.grid_w - 2;
         a_cols = kPackK;
         a_rows = kPackLeadRows + 2 * (h->x2_group_elems / 48);
         L.a_row_bias = kPackLeadRows;
@@ -275,41 +283,28 @@ int setup_layer(svx_handle* h, int li, const __half* a_hi, const __half* a_lo, l
     L.m_rows = 0;
     L.bias = h->bias[li];
     L.relu = 1;
-    L.out_f32 = out_f32;
-    L.out_hi = out_hi;
-    L.out_lo = out_lo;
-    L.ldc = ldc;
-    L.pos_per_img = pos_per_img;
-    L.grid_w = grid_w;
-    L.valid_h = valid_h;
-    L.valid_w = valid_w;
-    int a_box_rows = GEMM_BLOCK_M, b_box_rows = s.block_n;
-    if (h->use_slab && h->use_pair && s.block_n_pair > 0) {
-        L.block_n = s.block_n_pair;
-        { const char* e = std::getenv("SVX_STG8"); L.allow_stg8 = e ? std::atoi(e) : 1; }   // SVX_STG8=0: A/B
-        if ((rc = plan_slab_pair(L))) return rc;
-        if (const char* e = std::getenv("SVX_ACC")) L.acc_bufs = std::atoi(e);   // development A/B
-        L.desc_base_offset_mode = h->desc_bo_mode;
-        a_box_rows = L.slab_rows;
-        b_box_rows = L.block_n / 2;
-    } else if (h->use_slab) {
-        if ((rc = plan_slab(L))) return rc;
-        L.desc_base_offset_mode = h->desc_bo_mode;
-        a_box_rows = L.slab_rows;
-    }
-    if ((rc = make_tensor_map_2d(&L.tm_a_hi, a_hi, a_rows, a_cols, lda, a_box_rows))) return rc;
-    if ((rc = make_tensor_map_2d(&L.tm_a_lo, a_lo ? a_lo : a_hi, a_rows, a_cols, lda, a_box_rows))) return rc;
-    if ((rc = make_tensor_map_2d(&L.tm_b_hi, h->w_hi[li], s.n_total, K, K, b_box_rows))) return rc;
-    if ((rc = make_tensor_map_2d(&L.tm_b_lo, h->w_lo[li], s.n_total, K, K, b_box_rows))) return rc;
+    L.out_f32 = io.out_f32;
+    L.out_hi = io.out_hi;
+    L.out_lo = io.out_lo;
+    L.ldc = io.ldc;
+    L.pos_per_img = io.pos_per_img;
+    L.grid_w = io.grid_w;
+    L.valid_h = io.valid_h;
+    L.valid_w = io.valid_w;
+    L.pool_out = io.pool;
+    L.pool_out2 = io.pool2;
+    L.pool_h = io.pool_h;
+    L.pool_w = io.pool_w;
+    if ((rc = plan_layer(L))) return rc;
+    if ((rc = make_tensor_map_2d(&L.tm_a_hi, a_hi, a_rows, a_cols, io.lda, L.slab_rows))) return rc;
+    if ((rc = make_tensor_map_2d(&L.tm_a_lo, a_lo ? a_lo : a_hi, a_rows, a_cols, io.lda, L.slab_rows))) return rc;
+    if ((rc = make_tensor_map_2d(&L.tm_b_hi, h->w_hi[li], s.n_total, K, K, L.block_n / 2))) return rc;
+    if ((rc = make_tensor_map_2d(&L.tm_b_lo, h->w_lo[li], s.n_total, K, K, L.block_n / 2))) return rc;
+    if (h->dbg) L.dbg = h->dbg + li * 8;
     return 0;
 }
 
-int run_layer(svx_handle* h, int li, cudaStream_t st) {
-    const GemmLayer& L = h->layer[li];
-    if (L.use_slab == 2) return launch_conv_layer_pair(L, h->num_sms, st);
-    if (L.use_slab == 1) return launch_conv_layer(L, h->num_sms, st);
-    return launch_gemm_layer(L, h->num_sms, st);
-}
+int run_layer(svx_handle* h, int li, cudaStream_t st) { return launch_layer(h->layer[li], h->num_sms, st); }
 
 int build_model(svx_handle* h, const svx_weights* w) {
     const long long B = h->max_batch;
@@ -346,56 +341,58 @@ int build_model(svx_handle* h, const svx_weights* w) {
         if ((rc = dev_alloc(h, &h->front_scratch, (size_t)h->front_blocks * 640 * 96, false))) return rc;
     }
 
-    // activations: zero once; pad positions/channels are never written afterwards
-    if ((rc = dev_alloc(h, &h->y1, (size_t)B * P1 * 96))) return rc;
-    size_t x2_elems = (size_t)B * P2 * 128;
-    if (h->use_pack) {
-        // packed: two group planes of [B*841 + 64 zero rows][48]; the zero rows are the top padding
-        // of the next plane and absorb the 256-wide over-read of the last positions
-        h->x2_ld = 48;
-        h->x2_group_elems = ((long long)B * P2 + 64) * 48;
-        x2_elems = (size_t)(kPackLeadRows * 48 + 2 * h->x2_group_elems + 256);
-    }
+    // activations: zero once; pad positions/channels are never written afterwards.
+    // x2: two group planes of [B*841 + 64 zero rows][48]; the zero rows are the top padding of the
+    // next plane and absorb the 256-wide over-read of the last positions
+    h->x2_ld = 48;
+    h->x2_group_elems = ((long long)B * P2 + 64) * 48;
+    const size_t x2_elems = (size_t)(kPackLeadRows * 48 + 2 * h->x2_group_elems + 256);
     if ((rc = dev_alloc(h, &h->x2_hi, x2_elems))) return rc;
     if ((rc = dev_alloc(h, &h->x2_lo, x2_elems))) return rc;
-    if (h->use_pack) {                           // data pointers start after the leading zero rows
-        h->x2_hi += (size_t)kPackLeadRows * 48;
-        h->x2_lo += (size_t)kPackLeadRows * 48;
-    }
-    if ((rc = dev_alloc(h, &h->y2, (size_t)B * P2 * 256))) return rc;
+    h->x2_hi += (size_t)kPackLeadRows * 48;       // data pointers start after the leading zero rows
+    h->x2_lo += (size_t)kPackLeadRows * 48;
+    if ((rc = dev_alloc(h, &h->p2, (size_t)B * 169 * 256))) return rc;
+    if ((rc = dev_alloc(h, &h->p2b, (size_t)B * 169 * 256))) return rc;
     if ((rc = dev_alloc(h, &h->x3_hi, (size_t)B * P3 * 256))) return rc;
     if ((rc = dev_alloc(h, &h->x3_lo, (size_t)B * P3 * 256))) return rc;
     if ((rc = dev_alloc(h, &h->x4_hi, (size_t)B * P3 * 384))) return rc;
     if ((rc = dev_alloc(h, &h->x4_lo, (size_t)B * P3 * 384))) return rc;
     if ((rc = dev_alloc(h, &h->x5_hi, (size_t)B * P3 * 384))) return rc;
     if ((rc = dev_alloc(h, &h->x5_lo, (size_t)B * P3 * 384))) return rc;
-    if ((rc = dev_alloc(h, &h->y5, (size_t)B * P3 * 256))) return rc;
+    if ((rc = dev_alloc(h, &h->p5, (size_t)B * 36 * 256))) return rc;
+    if ((rc = dev_alloc(h, &h->p5b, (size_t)B * 36 * 256))) return rc;
     if ((rc = dev_alloc(h, &h->x6_hi, (size_t)B * 9216))) return rc;
     if ((rc = dev_alloc(h, &h->x6_lo, (size_t)B * 9216))) return rc;
     if ((rc = dev_alloc(h, &h->x7_hi, (size_t)B * 4096))) return rc;
     if ((rc = dev_alloc(h, &h->x7_lo, (size_t)B * 4096))) return rc;
     if ((rc = dev_alloc(h, &h->x8_hi, (size_t)B * 4096))) return rc;
     if ((rc = dev_alloc(h, &h->x8_lo, (size_t)B * 4096))) return rc;
-
-    //                 layer    A hi      A lo      A rows  lda grid center out_f32 out_hi    out_lo   ldc  pos  vh  vw
-    if ((rc = setup_layer(h, L_CONV1, h->x1, nullptr, B * P1, 64, S2D, 0, h->y1, nullptr, nullptr, 96, 0, 0, 0))) return rc;
-    {   // conv2's outputs at pad positions (13 % of y2) are not stored: pool2 reads valid positions
-        // only (SVX_Y2MASK=0 restores the unmasked store for A/B: 849 -> 845 clk per k-block)
-        const char* e = std::getenv("SVX_Y2MASK");
-        const bool mask = !(e && std::atoi(e) == 0);
-        if ((rc = setup_layer(h, L_CONV2, h->x2_hi, h->x2_lo, B * P2, h->x2_ld, G2, 2, h->y2, nullptr, nullptr, 256,
-                              mask ? P2 : 0, mask ? 27 : 0, mask ? 27 : 0))) return rc;
-    }
-    if ((rc = setup_layer(h, L_CONV3, h->x3_hi, h->x3_lo, B * P3, 256, G3, 1, nullptr, h->x4_hi, h->x4_lo, 384, P3, 13, 13))) return rc;
-    if ((rc = setup_layer(h, L_CONV4, h->x4_hi, h->x4_lo, B * P3, 384, G3, 1, nullptr, h->x5_hi, h->x5_lo, 384, P3, 13, 13))) return rc;
-    if ((rc = setup_layer(h, L_CONV5, h->x5_hi, h->x5_lo, B * P3, 384, G3, 1, h->y5, nullptr, nullptr, 256, 0, 0, 0))) return rc;
-    if ((rc = setup_layer(h, L_FC6, h->x6_hi, h->x6_lo, B, 9216, 1, 0, nullptr, h->x7_hi, h->x7_lo, 4096, 0, 0, 0))) return rc;
-    if ((rc = setup_layer(h, L_FC7, h->x7_hi, h->x7_lo, B, 4096, 1, 0, nullptr, h->x8_hi, h->x8_lo, 4096, 0, 0, 0))) return rc;
-    if (std::getenv("SVX_DBG")) {
+    if (std::getenv("SVX_DBG")) {                 // per-role cycle counters (svx_debug_counters)
         if ((rc = dev_alloc(h, &h->dbg, (size_t)L_COUNT * 8))) return rc;
-        for (int li = 0; li < L_COUNT; ++li) h->layer[li].dbg = h->dbg + li * 8;
     }
+
+    //                                   A hi      A lo      A rows  lda       grid c  f32      hi        lo        ldc  pos vh  vw  pool            ph  pw
+    if ((rc = setup_layer(h, L_CONV2, {h->x2_hi, h->x2_lo, B * P2, h->x2_ld, G2, 2, nullptr, nullptr, nullptr, 256, P2, 27, 27, h->p2, h->p2b, 13, 13}))) return rc;
+    if ((rc = setup_layer(h, L_CONV3, {h->x3_hi, h->x3_lo, B * P3, 256, G3, 1, nullptr, h->x4_hi, h->x4_lo, 384, P3, 13, 13, nullptr, nullptr, 0, 0}))) return rc;
+    if ((rc = setup_layer(h, L_CONV4, {h->x4_hi, h->x4_lo, B * P3, 384, G3, 1, nullptr, h->x5_hi, h->x5_lo, 384, P3, 13, 13, nullptr, nullptr, 0, 0}))) return rc;
+    if ((rc = setup_layer(h, L_CONV5, {h->x5_hi, h->x5_lo, B * P3, 384, G3, 1, nullptr, nullptr, nullptr, 256, P3, 13, 13, h->p5, h->p5b, 6, 6}))) return rc;
+    if ((rc = setup_layer(h, L_FC6, {h->x6_hi, h->x6_lo, B, 9216, 1, 0, nullptr, h->x7_hi, h->x7_lo, 4096, 0, 0, 0, nullptr, nullptr, 0, 0}))) return rc;
+    if ((rc = setup_layer(h, L_FC7, {h->x7_hi, h->x7_lo, B, 4096, 1, 0, nullptr, h->x8_hi, h->x8_lo, 4096, 0, 0, 0, nullptr, nullptr, 0, 0}))) return rc;
     h->has_model = true;
+    return 0;
+}
+
+// The dense conv1 path of svx_forward (arbitrary images): its buffers exist only once it is used.
+int ensure_dense_path(svx_handle* h) {
+    if (h->x1) return 0;
+    const long long D = h->max_batch < kDenseBatch ? h->max_batch : kDenseBatch;
+    int rc;
+    if ((rc = dev_alloc(h, &h->x1, (size_t)D * P1 * 64))) return rc;
+    if ((rc = dev_alloc(h, &h->y1, (size_t)D * P1 * 96))) return rc;
+    // conv1's activations (pixel values) are exact in fp16: no lo plane, two passes
+    if ((rc = setup_layer(h, L_CONV1, {h->x1, nullptr, D * P1, 64, S2D, 0, h->y1, nullptr, nullptr, 96, 0, 0, 0, nullptr, nullptr, 0, 0}))) return rc;
+    SVX_CUDA_CHECK(cudaDeviceSynchronize());
+    h->dense_batch = D;
     return 0;
 }
 
@@ -429,46 +426,27 @@ int profile_collect(svx_handle* h) {
     return 0;
 }
 
-// x1 (conv1 operand) of `n` sites is resident -> labels / probs / logits
+// conv2 operand (x2) of `n` sites is resident -> labels / probs / logits / calls
 int run_cnn(svx_handle* h, long long n, int32_t* labels, float* probs, float* logits,
-            cudaStream_t st, bool x2_ready = false, const CallSinks* sinks = nullptr) {
+            cudaStream_t st, const CallSinks* sinks = nullptr) {
     int rc;
-    const long long rows[L_COUNT] = {n * P1, n * P2, n * P3, n * P3, n * P3, n, n};
-    for (int li = 0; li < L_COUNT; ++li) h->layer[li].m_rows = rows[li];
-
-    if (!x2_ready) {
-    mark(h, 1, st);
-    if ((rc = run_layer(h, L_CONV1, st))) return rc;
-    PoolParams p1{};
-    p1.in = h->y1; p1.in_grid_w = S2D; p1.in_pos_per_img = P1; p1.C = 96; p1.out_h = 27; p1.out_w = 27;
-    p1.lrn = 1; p1.out_hi = h->x2_hi; p1.out_lo = h->x2_lo; p1.out_ld = h->x2_ld; p1.out_grid_w = G2;
-    p1.out_pos_per_img = P2; p1.group_real = 48; p1.group_elems = h->x2_group_elems; p1.flatten = 0;
-    mark(h, 2, st);
-    if ((rc = launch_pool(p1, n, h->num_sms, st))) return rc;
-    }
+    const long long rows[L_COUNT] = {0, n * P2, n * P3, n * P3, n * P3, n, n};
+    for (int li = L_CONV2; li < L_COUNT; ++li) h->layer[li].m_rows = rows[li];
 
     mark(h, 3, st);
-    if ((rc = run_layer(h, L_CONV2, st))) return rc;
-    PoolParams p2{};
-    p2.in = h->y2; p2.in_grid_w = G2; p2.in_pos_per_img = P2; p2.C = 256; p2.out_h = 13; p2.out_w = 13;
-    p2.lrn = 1; p2.out_hi = h->x3_hi; p2.out_lo = h->x3_lo; p2.out_ld = 256; p2.out_grid_w = G3;
-    p2.out_pos_per_img = P3; p2.group_real = 256; p2.group_elems = 256; p2.flatten = 0;
+    if ((rc = run_layer(h, L_CONV2, st))) return rc;             // + ReLU + pool2 (window maxima -> p2)
     mark(h, 4, st);
-    if ((rc = launch_pool(p2, n, h->num_sms, st))) return rc;
-
+    const FinishParams f2{h->p2, h->p2b, P2, G2, 13, 13, 1, h->x3_hi, h->x3_lo, 256, G3, P3};
+    if ((rc = launch_finish_pooled(f2, n, h->num_sms, st))) return rc;   // LRN2 + hi/lo split
     mark(h, 5, st);
     if ((rc = run_layer(h, L_CONV3, st))) return rc;
     mark(h, 6, st);
     if ((rc = run_layer(h, L_CONV4, st))) return rc;
     mark(h, 7, st);
-    if ((rc = run_layer(h, L_CONV5, st))) return rc;
-    PoolParams p5{};
-    p5.in = h->y5; p5.in_grid_w = G3; p5.in_pos_per_img = P3; p5.C = 256; p5.out_h = 6; p5.out_w = 6;
-    p5.lrn = 0; p5.out_hi = h->x6_hi; p5.out_lo = h->x6_lo; p5.out_ld = 9216; p5.out_grid_w = 6;
-    p5.out_pos_per_img = 36; p5.group_real = 256; p5.group_elems = 256; p5.flatten = 1;
+    if ((rc = run_layer(h, L_CONV5, st))) return rc;             // + ReLU + pool5 (-> p5)
     mark(h, 8, st);
-    if ((rc = launch_pool(p5, n, h->num_sms, st))) return rc;
-
+    const FinishParams f5{h->p5, h->p5b, P3, G3, 6, 6, 0, h->x6_hi, h->x6_lo, 256, 6, 36};   // NHWC flatten (alexnet.py:49)
+    if ((rc = launch_finish_pooled(f5, n, h->num_sms, st))) return rc;
     mark(h, 9, st);
     if ((rc = run_layer(h, L_FC6, st))) return rc;
     mark(h, 10, st);
@@ -482,15 +460,27 @@ int run_cnn(svx_handle* h, long long n, int32_t* labels, float* probs, float* lo
     return 0;
 }
 
-// rows -> conv2 operand (fused sparse front end) or rows -> conv1 operand (dense path)
+// rows -> conv2 operand: the fused sparse front end (encode + conv1 + ReLU + pool1 + LRN1)
 int encode_front(svx_handle* h, const int32_t* rows_dev, long long m, cudaStream_t st) {
-    if (h->use_front) {
-        static const int front_flags = [] { const char* e = std::getenv("SVX_FRONT_FLAGS"); return e ? std::atoi(e) : 3; }();
-        FrontParams fp{h->front_w255, h->front_base, h->x2_hi, h->x2_lo, h->front_scratch, h->front_blocks,
-                       h->x2_ld, h->x2_group_elems, front_flags};
-        return launch_front(rows_dev, m, fp, h->num_sms, st);
-    }
-    return launch_encode(rows_dev, m, h->x1, 2, h->num_sms, st);
+    FrontParams fp{h->front_w255, h->front_base, h->x2_hi, h->x2_lo, h->front_scratch, h->front_blocks,
+                   h->x2_ld, h->x2_group_elems, 3};
+    mark(h, 0, st);
+    return launch_front(rows_dev, m, fp, h->num_sms, st);
+}
+
+// images -> conv2 operand: space-to-depth, dense tcgen05 conv1, pool1 + LRN1 (svx_forward)
+int dense_front(svx_handle* h, const void* images, int dtype, long long m, cudaStream_t st) {
+    int rc;
+    if ((rc = launch_nhwc_to_s2d(images, dtype, m, h->x1, st))) return rc;
+    h->layer[L_CONV1].m_rows = m * P1;
+    mark(h, 1, st);
+    if ((rc = run_layer(h, L_CONV1, st))) return rc;
+    PoolParams p1{};
+    p1.in = h->y1; p1.in_grid_w = S2D; p1.in_pos_per_img = P1; p1.C = 96; p1.out_h = 27; p1.out_w = 27;
+    p1.lrn = 1; p1.out_hi = h->x2_hi; p1.out_lo = h->x2_lo; p1.out_ld = h->x2_ld; p1.out_grid_w = G2;
+    p1.out_pos_per_img = P2; p1.group_real = 48; p1.group_elems = h->x2_group_elems; p1.flatten = 0;
+    mark(h, 2, st);
+    return launch_pool(p1, m, h->num_sms, st);
 }
 
 }  // namespace
@@ -508,7 +498,9 @@ int svx_create(const svx_weights* weights, int device, int64_t max_batch, int pr
                svx_handle** out) {
     if (!out) return fail(SVX_ERR_INVALID, "svx_create: out is NULL");
     *out = nullptr;
-    if (max_batch <= 0 || max_batch > (1 << 20)) return fail(SVX_ERR_INVALID, "svx_create: bad max_batch");
+    if (max_batch <= 0 || max_batch > kMaxBatchLimit)
+        return fail(SVX_ERR_INVALID, "svx_create: max_batch must be in [1, " + std::to_string(kMaxBatchLimit) +
+                                         "] (the workspaces take ~1.4 MB of HBM per site)");
     if (precision != SVX_PRECISION_3PASS && precision != SVX_PRECISION_1PASS)
         return fail(SVX_ERR_INVALID, "svx_create: bad precision");
     int ndev = 0;
@@ -523,12 +515,6 @@ int svx_create(const svx_weights* weights, int device, int64_t max_batch, int pr
                                              "' is not sm_100 (this library has no other code path)");
     std::unique_ptr<svx_handle> h(new svx_handle());
     h->device = device;
-    if (const char* e = std::getenv("SVX_SLAB")) h->use_slab = std::atoi(e) != 0;
-    if (const char* e = std::getenv("SVX_FRONT")) h->use_front = std::atoi(e) != 0;
-    if (const char* e = std::getenv("SVX_PAIR")) h->use_pair = std::atoi(e) != 0;
-    if (const char* e = std::getenv("SVX_PACK")) h->use_pack = std::atoi(e) != 0;
-    if (!h->use_slab) h->use_pack = false;            // the per-tap kernel has no partial k-blocks
-    if (const char* e = std::getenv("SVX_DESC_BO")) h->desc_bo_mode = std::atoi(e);
     h->num_sms = prop.multiProcessorCount;
     h->max_batch = max_batch;
     h->precision = precision;
@@ -544,10 +530,7 @@ int svx_create(const svx_weights* weights, int device, int64_t max_batch, int pr
     if ((rc = dev_alloc(h.get(), &h->rows_dev, (size_t)max_batch * SVX_ROW_FIELDS))) return cleanup(rc);
     if ((rc = dev_alloc(h.get(), &h->labels_dev, (size_t)max_batch))) return cleanup(rc);
     if ((rc = dev_alloc(h.get(), &h->probs_dev, (size_t)max_batch * SVX_NUM_CLASSES))) return cleanup(rc);
-    if (weights) {
-        if ((rc = dev_alloc(h.get(), &h->x1, (size_t)max_batch * P1 * 64))) return cleanup(rc);
-        if ((rc = build_model(h.get(), weights))) return cleanup(rc);
-    }
+    if (weights && (rc = build_model(h.get(), weights))) return cleanup(rc);
     cudaError_t e = cudaDeviceSynchronize();
     if (e != cudaSuccess) return cleanup(fail(SVX_ERR_CUDA, std::string("svx_create: ") + cudaGetErrorString(e)));
     *out = h.release();
@@ -615,12 +598,13 @@ int svx_forward(svx_handle* h, const void* images_dev, int dtype, int64_t n, flo
     DeviceGuard guard(h->device);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const size_t esz = dtype == SVX_IMAGE_F32 ? 4 : 2;
+    int rc;
+    if ((rc = ensure_dense_path(h))) return rc;
     SVX_CUDA_CHECK(cudaStreamWaitEvent(st, h->busy, 0));        // workspaces free of earlier entries
-    for (int64_t s = 0; s < n; s += h->max_batch) {
-        const int64_t m = n - s < h->max_batch ? n - s : h->max_batch;
+    for (int64_t s = 0; s < n; s += h->dense_batch) {
+        const int64_t m = n - s < h->dense_batch ? n - s : h->dense_batch;
         const char* src = static_cast<const char*>(images_dev) + (size_t)s * SVX_IMG * SVX_IMG * 3 * esz;
-        int rc;
-        if ((rc = launch_nhwc_to_s2d(src, dtype, m, h->x1, st))) return rc;
+        if ((rc = dense_front(h, src, dtype, m, st))) return rc;
         if ((rc = run_cnn(h, m, h->labels_dev, h->probs_dev, logits_dev + s * SVX_NUM_CLASSES, st))) return rc;
     }
     SVX_CUDA_CHECK(cudaEventRecord(h->busy, st));
@@ -638,10 +622,9 @@ int svx_classify_device(svx_handle* h, const int32_t* rows_dev, int64_t n, int32
     for (int64_t s = 0; s < n; s += h->max_batch) {
         const int64_t m = n - s < h->max_batch ? n - s : h->max_batch;
         int rc;
-        mark(h, 0, st);
         if ((rc = encode_front(h, rows_dev + s * SVX_ROW_FIELDS, m, st))) return rc;
         if ((rc = run_cnn(h, m, labels_dev + s, probs_dev + s * SVX_NUM_CLASSES,
-                          logits_dev ? logits_dev + s * SVX_NUM_CLASSES : nullptr, st, h->use_front)))
+                          logits_dev ? logits_dev + s * SVX_NUM_CLASSES : nullptr, st)))
             return rc;
     }
     SVX_CUDA_CHECK(cudaEventRecord(h->busy, st));
@@ -661,9 +644,8 @@ int svx_classify(svx_handle* h, const int32_t* rows_host, int64_t n, int32_t* la
         int rc;
         SVX_CUDA_CHECK(cudaMemcpyAsync(h->rows_dev, rows_host + s * SVX_ROW_FIELDS,
                                        (size_t)m * SVX_ROW_FIELDS * sizeof(int32_t), cudaMemcpyHostToDevice, st));
-        mark(h, 0, st);
         if ((rc = encode_front(h, h->rows_dev, m, st))) return rc;
-        if ((rc = run_cnn(h, m, h->labels_dev, h->probs_dev, nullptr, st, h->use_front))) return rc;
+        if ((rc = run_cnn(h, m, h->labels_dev, h->probs_dev, nullptr, st))) return rc;
         SVX_CUDA_CHECK(cudaMemcpyAsync(labels_host + s, h->labels_dev, (size_t)m * sizeof(int32_t),
                                        cudaMemcpyDeviceToHost, st));
         SVX_CUDA_CHECK(cudaMemcpyAsync(probs_host + s * SVX_NUM_CLASSES, h->probs_dev,
@@ -688,9 +670,8 @@ int svx_classify_device_calls(svx_handle* h, const int32_t* rows_dev, int64_t n,
         CallSinks sinks = {};
         sinks.count = 1;
         sinks.ptr[0] = reinterpret_cast<int2*>(calls_dev + s);
-        mark(h, 0, st);
         if ((rc = encode_front(h, rows_dev + s * SVX_ROW_FIELDS, m, st))) return rc;
-        if ((rc = run_cnn(h, m, nullptr, nullptr, nullptr, st, h->use_front, &sinks))) return rc;
+        if ((rc = run_cnn(h, m, nullptr, nullptr, nullptr, st, &sinks))) return rc;
     }
     SVX_CUDA_CHECK(cudaEventRecord(h->busy, st));
     return SVX_OK;
@@ -713,13 +694,19 @@ int svx_exchange_create(svx_handle* h, int rank, int world, int64_t sites_per_ra
     // plain cudaMalloc (not a pool): the allocation is exported with cudaIpcGetMemHandle
     cudaError_t e = cudaMalloc(&x->local, bytes);
     if (e != cudaSuccess) return fail(SVX_ERR_NOMEM, std::string("svx_exchange_create: ") + cudaGetErrorString(e));
-    auto cleanup = [&](int rc) { cudaFree(x->local); cudaFree(x->done); return rc; };
+    auto cleanup = [&](int rc) {
+        cudaFree(x->local); cudaFree(x->done);
+        if (x->error_host) cudaFreeHost(x->error_host);
+        return rc;
+    };
     if ((e = cudaMemset(x->local, 0, bytes)) != cudaSuccess ||
-        (e = cudaMalloc(reinterpret_cast<void**>(&x->done), 2 * sizeof(unsigned int))) != cudaSuccess ||
-        (e = cudaMemset(x->done, 0, 2 * sizeof(unsigned int))) != cudaSuccess ||
+        (e = cudaMalloc(reinterpret_cast<void**>(&x->done), sizeof(unsigned int))) != cudaSuccess ||
+        (e = cudaMemset(x->done, 0, sizeof(unsigned int))) != cudaSuccess ||
+        (e = cudaHostAlloc(reinterpret_cast<void**>(&x->error_host), sizeof(unsigned int), cudaHostAllocMapped)) != cudaSuccess ||
+        (e = cudaHostGetDevicePointer(reinterpret_cast<void**>(&x->error), x->error_host, 0)) != cudaSuccess ||
         (e = cudaDeviceSynchronize()) != cudaSuccess)
         return cleanup(fail(SVX_ERR_CUDA, std::string("svx_exchange_create: ") + cudaGetErrorString(e)));
-    x->error = x->done + 1;
+    *x->error_host = 0;
     x->base[rank] = x->local;
     x->attached = world == 1;
     *out = x.release();
@@ -760,6 +747,11 @@ int svx_classify_exchange(svx_handle* h, svx_exchange* x, const int32_t* rows_de
     if (!x->attached) return fail(SVX_ERR_INVALID, "svx_classify_exchange: exchange is not attached");
     if (n <= 0 || n > x->per_rank || !rows_dev)
         return fail(SVX_ERR_INVALID, "svx_classify_exchange: need 0 < n <= sites_per_rank (pad the shard)");
+    // a timeout of an earlier call is sticky: the gathered buffers of that call (and possibly of this
+    // one) hold poisoned calls (label -1) for the rank that did not show up
+    if (const unsigned int err = *static_cast<volatile unsigned int*>(x->error_host))
+        return fail(SVX_ERR_CUDA, "svx_classify_exchange: an earlier exchange timed out waiting for rank " +
+                                      std::to_string(err - 1) + " (svx_exchange_status clears the error)");
     DeviceGuard guard(h->device);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     SVX_CUDA_CHECK(cudaStreamWaitEvent(st, h->busy, 0));
@@ -778,12 +770,12 @@ int svx_classify_exchange(svx_handle* h, svx_exchange* x, const int32_t* rows_de
             sinks.epoch = epoch;
             sinks.done = x->done;
         }
-        mark(h, 0, st);
         if ((rc = encode_front(h, rows_dev + s * SVX_ROW_FIELDS, m, st))) return rc;
-        if ((rc = run_cnn(h, m, nullptr, nullptr, nullptr, st, h->use_front, &sinks))) return rc;
+        if ((rc = run_cnn(h, m, nullptr, nullptr, nullptr, st, &sinks))) return rc;
     }
     int rc;
-    if ((rc = launch_exchange_wait(x->flags(x->rank), x->world, epoch, x->timeout_ns, x->error, st))) return rc;
+    if ((rc = launch_exchange_wait(x->flags(x->rank), x->world, epoch, x->timeout_ns, x->error,
+                                   reinterpret_cast<int2*>(x->region(x->rank, parity)), x->per_rank, st))) return rc;
     SVX_CUDA_CHECK(cudaEventRecord(h->busy, st));
     if (gathered_dev) *gathered_dev = reinterpret_cast<const svx_call*>(x->region(x->rank, parity));
     return SVX_OK;
@@ -792,12 +784,12 @@ int svx_classify_exchange(svx_handle* h, svx_exchange* x, const int32_t* rows_de
 int svx_exchange_status(svx_exchange* x) {
     if (!x) return fail(SVX_ERR_INVALID, "svx_exchange_status: NULL exchange");
     DeviceGuard guard(x->device);
-    unsigned int err = 0;
     SVX_CUDA_CHECK(cudaDeviceSynchronize());
-    SVX_CUDA_CHECK(cudaMemcpy(&err, x->error, sizeof(err), cudaMemcpyDeviceToHost));
+    const unsigned int err = *static_cast<volatile unsigned int*>(x->error_host);
     if (err != 0) {
-        SVX_CUDA_CHECK(cudaMemset(x->error, 0, sizeof(err)));
-        return fail(SVX_ERR_CUDA, "svx_classify_exchange: timed out waiting for rank " + std::to_string(err - 1));
+        *x->error_host = 0;
+        return fail(SVX_ERR_CUDA, "svx_classify_exchange: timed out waiting for rank " + std::to_string(err - 1) +
+                                      "; its calls in the gathered buffer are poisoned (label -1)");
     }
     return SVX_OK;
 }
@@ -810,6 +802,7 @@ void svx_exchange_destroy(svx_exchange* x) {
         if (x->opened[r]) cudaIpcCloseMemHandle(x->base[r]);
     cudaFree(x->local);
     cudaFree(x->done);
+    if (x->error_host) cudaFreeHost(x->error_host);
     delete x;
 }
 
@@ -820,19 +813,19 @@ int svx_debug_activation(svx_handle* h, const char* name, int64_t n, float* out_
     SVX_CUDA_CHECK(cudaDeviceSynchronize());
     struct Src { const char* name; const float* f32; const __half* hi; const __half* lo; int pos, grid_w, H, W, ld, C, greal; long long gelems; };
     const Src table[] = {
-        {"conv1", h->y1, nullptr, nullptr, P1, S2D, 55, 55, 96, 96, 96, 96},
+        {"conv1", h->y1, nullptr, nullptr, P1, S2D, 55, 55, 96, 96, 96, 96},      // svx_forward only
         {"norm1", nullptr, h->x2_hi, h->x2_lo, P2, G2, 27, 27, h->x2_ld, 96, 48, h->x2_group_elems},
-        {"conv2", h->y2, nullptr, nullptr, P2, G2, 27, 27, 256, 256, 256, 256},
         {"norm2", nullptr, h->x3_hi, h->x3_lo, P3, G3, 13, 13, 256, 256, 256, 256},
         {"conv3", nullptr, h->x4_hi, h->x4_lo, P3, G3, 13, 13, 384, 384, 384, 384},
         {"conv4", nullptr, h->x5_hi, h->x5_lo, P3, G3, 13, 13, 384, 384, 384, 384},
-        {"conv5", h->y5, nullptr, nullptr, P3, G3, 13, 13, 256, 256, 256, 256},
         {"pool5", nullptr, h->x6_hi, h->x6_lo, 36, 6, 6, 6, 256, 256, 256, 256},
         {"fc6", nullptr, h->x7_hi, h->x7_lo, 1, 1, 1, 1, 4096, 4096, 4096, 4096},
         {"fc7", nullptr, h->x8_hi, h->x8_lo, 1, 1, 1, 1, 4096, 4096, 4096, 4096},
     };
     for (const Src& s : table) {
         if (std::strcmp(s.name, name) != 0) continue;
+        if (!s.f32 && !s.hi) return fail(SVX_ERR_INVALID, "svx_debug_activation: 'conv1' exists only after svx_forward");
+        if (s.f32 && n > h->dense_batch) return fail(SVX_ERR_INVALID, "svx_debug_activation: n exceeds the dense-path batch");
         const int ngroups = s.C / s.greal;
         const size_t count = (size_t)(ngroups - 1) * (size_t)s.gelems + ((size_t)n * s.pos - 1) * s.ld + s.greal;
         std::vector<float> buf(count);
@@ -857,60 +850,15 @@ int svx_debug_activation(svx_handle* h, const char* name, int64_t n, float* out_
     return fail(SVX_ERR_INVALID, std::string("svx_debug_activation: unknown activation '") + name + "'");
 }
 
-int svx_gemm_selftest(int device, const float* a_dev, const float* b_dev, float* c_dev, int64_t m,
-                      int64_t n, int64_t k, int block_n, int precision, void* stream) {
-    if (!a_dev || !b_dev || !c_dev || m <= 0 || n <= 0 || k <= 0)
-        return fail(SVX_ERR_INVALID, "svx_gemm_selftest: bad arguments");
-    if (k % GEMM_BLOCK_K != 0 || n % block_n != 0)
-        return fail(SVX_ERR_INVALID, "svx_gemm_selftest: k must be a multiple of 64 and n of block_n");
+// Shared by the two self-test entries: fp32 operands on the device -> hi/lo planes -> one launch of
+// the layer kernel with `taps` row offsets -> fp32 result.
+static int layer_selftest(int device, const float* a_dev, const float* b_dev, float* c_dev, int64_t m,
+                          int64_t n, int64_t k_per_tap, int taps, const int* row_off, int block_n,
+                          int precision, cudaStream_t st) {
     DeviceGuard guard(device);
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
     cudaDeviceProp prop;
     SVX_CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
-    if (prop.major != 10) return fail(SVX_ERR_UNSUPPORTED, "svx_gemm_selftest: device is not sm_100");
-    __half *a_hi = nullptr, *a_lo = nullptr, *b_hi = nullptr, *b_lo = nullptr;
-    float* bias = nullptr;
-    auto free_all = [&](int rc) {
-        cudaStreamSynchronize(st);
-        cudaFree(a_hi); cudaFree(a_lo); cudaFree(b_hi); cudaFree(b_lo); cudaFree(bias);
-        return rc;
-    };
-    SVX_CUDA_CHECK(cudaMalloc(&a_hi, (size_t)m * k * 2));
-    SVX_CUDA_CHECK(cudaMalloc(&a_lo, (size_t)m * k * 2));
-    SVX_CUDA_CHECK(cudaMalloc(&b_hi, (size_t)n * k * 2));
-    SVX_CUDA_CHECK(cudaMalloc(&b_lo, (size_t)n * k * 2));
-    SVX_CUDA_CHECK(cudaMalloc(&bias, (size_t)n * 4));
-    SVX_CUDA_CHECK(cudaMemsetAsync(bias, 0, (size_t)n * 4, st));
-    int rc;
-    if ((rc = launch_split_hilo(a_dev, m * k, a_hi, a_lo, st))) return free_all(rc);
-    if ((rc = launch_split_hilo(b_dev, n * k, b_hi, b_lo, st))) return free_all(rc);
-    GemmLayer L;
-    std::memset(&L, 0, sizeof(L));
-    if ((rc = make_tensor_map_2d(&L.tm_a_hi, a_hi, m, k, k, GEMM_BLOCK_M))) return free_all(rc);
-    if ((rc = make_tensor_map_2d(&L.tm_a_lo, a_lo, m, k, k, GEMM_BLOCK_M))) return free_all(rc);
-    if ((rc = make_tensor_map_2d(&L.tm_b_hi, b_hi, n, k, k, block_n))) return free_all(rc);
-    if ((rc = make_tensor_map_2d(&L.tm_b_lo, b_lo, n, k, k, block_n))) return free_all(rc);
-    L.block_n = block_n; L.chunk_kblocks = chunk_kblocks(); L.groups = 1; L.n_per_group = (int)n; L.taps = 1; L.cblocks = (int)(k / GEMM_BLOCK_K);
-    L.a_group_cols = 0; L.row_off[0] = 0;
-    L.use_a_lo = L.use_b_lo = precision == SVX_PRECISION_3PASS ? 1 : 0;
-    L.m_rows = m; L.bias = bias; L.relu = 0; L.out_f32 = c_dev; L.ldc = (int)n;
-    rc = launch_gemm_layer(L, prop.multiProcessorCount, st);
-    return free_all(rc);
-}
-
-int svx_conv_selftest(int device, const float* a_dev, const float* b_dev, float* c_dev, int64_t m,
-                      int64_t n, int64_t k_per_tap, int taps, const int* row_off, int block_n,
-                      int precision, int flags, void* stream) {
-    if (!a_dev || !b_dev || !c_dev || !row_off || m <= 0 || n <= 0 || k_per_tap <= 0 || taps < 1 ||
-        taps > GEMM_MAX_TAPS)
-        return fail(SVX_ERR_INVALID, "svx_conv_selftest: bad arguments");
-    if (k_per_tap % GEMM_BLOCK_K != 0 || n % block_n != 0)
-        return fail(SVX_ERR_INVALID, "svx_conv_selftest: k_per_tap % 64 or n % block_n != 0");
-    DeviceGuard guard(device);
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
-    cudaDeviceProp prop;
-    SVX_CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
-    if (prop.major != 10) return fail(SVX_ERR_UNSUPPORTED, "svx_conv_selftest: device is not sm_100");
+    if (prop.major != 10) return fail(SVX_ERR_UNSUPPORTED, "selftest: device is not sm_100");
     const int64_t k = k_per_tap * taps;
     __half *a_hi = nullptr, *a_lo = nullptr, *b_hi = nullptr, *b_lo = nullptr;
     float* bias = nullptr;
@@ -930,29 +878,42 @@ int svx_conv_selftest(int device, const float* a_dev, const float* b_dev, float*
     if ((rc = launch_split_hilo(b_dev, n * k, b_hi, b_lo, st))) return free_all(rc);
     GemmLayer L;
     std::memset(&L, 0, sizeof(L));
-    L.block_n = block_n; L.chunk_kblocks = chunk_kblocks(); L.groups = 1; L.n_per_group = (int)n;
+    L.block_n = block_n; L.chunk_kblocks = kChunkKBlocks; L.groups = 1; L.n_per_group = (int)n;
     L.taps = taps; L.cblocks = (int)(k_per_tap / GEMM_BLOCK_K); L.a_group_cols = 0;
+    L.last_ksteps = GEMM_BLOCK_K / 16;
     for (int t = 0; t < taps; ++t) L.row_off[t] = row_off[t];
     L.use_a_lo = L.use_b_lo = precision == SVX_PRECISION_3PASS ? 1 : 0;
     L.m_rows = m; L.bias = bias; L.relu = 0; L.out_f32 = c_dev; L.ldc = (int)n;
-    int a_box = GEMM_BLOCK_M, b_box = block_n;
-    if (flags & 4) {
-        if ((rc = plan_slab_pair(L))) return free_all(rc);
-        a_box = L.slab_rows;
-        b_box = block_n / 2;
-    } else if (flags & 1) {
-        if ((rc = plan_slab(L))) return free_all(rc);
-        L.desc_base_offset_mode = (flags >> 1) & 1;
-        a_box = L.slab_rows;
-    }
-    if ((rc = make_tensor_map_2d(&L.tm_a_hi, a_hi, m, k_per_tap, k_per_tap, a_box))) return free_all(rc);
-    if ((rc = make_tensor_map_2d(&L.tm_a_lo, a_lo, m, k_per_tap, k_per_tap, a_box))) return free_all(rc);
-    if ((rc = make_tensor_map_2d(&L.tm_b_hi, b_hi, n, k, k, b_box))) return free_all(rc);
-    if ((rc = make_tensor_map_2d(&L.tm_b_lo, b_lo, n, k, k, b_box))) return free_all(rc);
-    rc = (flags & 4) ? launch_conv_layer_pair(L, prop.multiProcessorCount, st)
-         : (flags & 1) ? launch_conv_layer(L, prop.multiProcessorCount, st)
-                       : launch_gemm_layer(L, prop.multiProcessorCount, st);
+    if ((rc = plan_layer(L))) return free_all(rc);
+    if ((rc = make_tensor_map_2d(&L.tm_a_hi, a_hi, m, k_per_tap, k_per_tap, L.slab_rows))) return free_all(rc);
+    if ((rc = make_tensor_map_2d(&L.tm_a_lo, a_lo, m, k_per_tap, k_per_tap, L.slab_rows))) return free_all(rc);
+    if ((rc = make_tensor_map_2d(&L.tm_b_hi, b_hi, n, k, k, block_n / 2))) return free_all(rc);
+    if ((rc = make_tensor_map_2d(&L.tm_b_lo, b_lo, n, k, k, block_n / 2))) return free_all(rc);
+    rc = launch_layer(L, prop.multiProcessorCount, st);
     return free_all(rc);
+}
+
+int svx_gemm_selftest(int device, const float* a_dev, const float* b_dev, float* c_dev, int64_t m,
+                      int64_t n, int64_t k, int block_n, int precision, void* stream) {
+    if (!a_dev || !b_dev || !c_dev || m <= 0 || n <= 0 || k <= 0)
+        return fail(SVX_ERR_INVALID, "svx_gemm_selftest: bad arguments");
+    if (k % GEMM_BLOCK_K != 0 || block_n <= 0 || n % block_n != 0)
+        return fail(SVX_ERR_INVALID, "svx_gemm_selftest: k must be a multiple of 64 and n of block_n");
+    const int zero = 0;
+    return layer_selftest(device, a_dev, b_dev, c_dev, m, n, k, 1, &zero, block_n, precision,
+                          static_cast<cudaStream_t>(stream));
+}
+
+int svx_conv_selftest(int device, const float* a_dev, const float* b_dev, float* c_dev, int64_t m,
+                      int64_t n, int64_t k_per_tap, int taps, const int* row_off, int block_n,
+                      int precision, void* stream) {
+    if (!a_dev || !b_dev || !c_dev || !row_off || m <= 0 || n <= 0 || k_per_tap <= 0 || taps < 1 ||
+        taps > GEMM_MAX_TAPS)
+        return fail(SVX_ERR_INVALID, "svx_conv_selftest: bad arguments");
+    if (k_per_tap % GEMM_BLOCK_K != 0 || block_n <= 0 || n % block_n != 0)
+        return fail(SVX_ERR_INVALID, "svx_conv_selftest: k_per_tap % 64 or n % block_n != 0");
+    return layer_selftest(device, a_dev, b_dev, c_dev, m, n, k_per_tap, taps, row_off, block_n, precision,
+                          static_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

@@ -56,58 +56,6 @@ def stage_encoder():
               f"{by/ms/1e6:.1f} GB/s algorithmic", flush=True)
 
 
-def stage_gemm():
-    torch.manual_seed(0)
-    cases = [(128, 128, 64, 128), (128, 128, 256, 128), (1000, 256, 512, 128), (300, 96, 192, 96),
-             (700, 384, 320, 64), (513, 512, 1024, 128), (4096, 4096, 4096, 128)]
-    for (m, n, k, bn) in cases:
-        a = torch.randn(m, k, device="cuda")
-        b = torch.randn(n, k, device="cuda") * 0.05
-        ref = (a.double() @ b.double().T)
-        for prec in ("1pass", "3pass"):
-            try:
-                c = C.gemm_selftest(a, b, block_n=bn, precision=prec)
-                torch.cuda.synchronize()
-                err = (c.double() - ref).abs().max().item()
-                print(f"gemm m={m} n={n} k={k} bn={bn} {prec}: max abs err {err:.3e} (ref max {ref.abs().max().item():.2f})", flush=True)
-            except Exception as ex:  # noqa: BLE001
-                print(f"gemm m={m} n={n} k={k} bn={bn} {prec}: FAILED {ex}", flush=True)
-                return
-
-
-def stage_slab():
-    torch.manual_seed(1)
-    cases = [  # (m, n, k_per_tap, offsets, block_n)
-        (600, 128, 64, [0, 1, 2, 57, 58, 59, 114, 115, 116], 128),
-        (1000, 96, 64, [0, 1, 2, 57, 58, 59, 114, 115, 116], 96),
-        (2000, 128, 64, [(kh - 2) * 29 + (kw - 2) for kh in range(5) for kw in range(5)], 128),
-        (900, 256, 192, [(kh - 1) * 14 + (kw - 1) for kh in range(3) for kw in range(3)], 128),
-        (700, 128, 256, [0], 64),
-        (5000, 512, 1024, [0], 128),
-    ]
-    for (m, n, k, offs, bn) in cases:
-        a = torch.randn(m, k, device="cuda")
-        b = torch.randn(n, k * len(offs), device="cuda") * 0.05
-        ref = torch.zeros(m, n, dtype=torch.float64, device="cuda")
-        ad = a.double()
-        for t, off in enumerate(offs):
-            sh = torch.zeros_like(ad)
-            lo, hi = max(0, -off), min(m, m - off)
-            sh[lo:hi] = ad[lo + off:hi + off]
-            ref += sh @ b[:, t * k:(t + 1) * k].double().T
-        for slab, pair in ((False, False), (True, False), (True, True)):
-            if pair and (n % 128 != 0):
-                continue
-            try:
-                c = C.conv_selftest(a, b, offs, block_n=(128 if pair else bn), precision="3pass", slab=slab, pair=pair)
-                torch.cuda.synchronize()
-                err = (c.double() - ref).abs().max().item()
-                print(f"conv m={m} n={n} k={k} taps={len(offs)} bn={bn} slab={slab} pair={pair}: max abs err {err:.3e} (ref max {ref.abs().max().item():.2f})", flush=True)
-            except Exception as ex:  # noqa: BLE001
-                print(f"conv m={m} n={n} k={k} taps={len(offs)} slab={slab} pair={pair}: FAILED {ex}", flush=True)
-                return
-
-
 def stage_cnn():
     from oracle import alexnet, encoder_c
     w = weights.synthetic_weights()
@@ -174,12 +122,14 @@ def stage_counters():
         prof = clf.profile_read(True)
         c = clf.debug_counters().astype(np.float64)
         names = ["conv1", "conv2", "conv3", "conv4", "conv5", "fc6", "fc7"]
-        print(f"[{prec}] slab={os.environ.get('SVX_SLAB','1')}  per-k-block cycles (avg over CTAs): total | wait operands | wait tmem | producer wait | epi: wait, drain, store (per k-block)   ms/launch")
+        print(f"[{prec}] per-k-block cycles (avg over CTAs): total | wait operands | wait tmem | producer wait | epi: wait, drain, store (per k-block)   ms/launch")
         for i, nm in enumerate(names):
             kb = max(c[i, 3], 1)
             print(f"  {nm:6s} kb/CTA={kb/iters/148:8.0f}  total={c[i,0]/kb:7.0f}  wait_op={c[i,1]/kb:7.0f}  wait_tm={c[i,2]/kb:7.0f}  prod_wait={c[i,4]/kb:7.0f}  epi_wait={c[i,5]/kb:7.0f} drain={c[i,6]/kb:7.0f} store={c[i,7]/kb:7.0f}   {prof[nm][0]/iters:.3f} ms", flush=True)
+        print("  other kernels, ms/launch: " + ", ".join(
+            f"{k} {prof[k][0]/iters:.3f}" for k in ("encode", "pool2_lrn2", "pool5", "fc8_softmax")), flush=True)
         clf.close()
 
 
 if __name__ == "__main__":
-    {"encoder": stage_encoder, "gemm": stage_gemm, "slab": stage_slab, "counters": stage_counters, "cnn": stage_cnn, "bench": stage_bench}[sys.argv[1]]()
+    {"encoder": stage_encoder, "counters": stage_counters, "cnn": stage_cnn, "bench": stage_bench}[sys.argv[1]]()
