@@ -111,9 +111,11 @@ __global__ void __launch_bounds__(256) pool_kernel(const PoolParams p, long long
 // pooled position, lane = 8 consecutive channels of 256.  Reads the window maximum (two parts where the
 // window straddles a 128-row chunk of the conv's rows), applies the LRN (conv2) and writes the fp16
 // hi/lo planes of the next layer's operand.  HBM bound: 1-2 KB read + 1 KB written per position.
+// Lane l owns channels [4l, 4l+4) and [128+4l, 128+4l+4): every load / store instruction of the warp
+// covers one contiguous 512-byte (fp32) or 256-byte (fp16) run.
 template <bool LRN>
 __global__ void __launch_bounds__(256) finish_pooled_kernel(const FinishParams p, long long total_pos) {
-    constexpr int U = 4;                                  // positions per warp and pass: 4 KB of loads in flight
+    constexpr int U = 2;                                  // positions per warp and pass
     const int lane = threadIdx.x & 31;
     const int warps_per_block = blockDim.x >> 5;
     const long long warp0 = (long long)blockIdx.x * warps_per_block + (threadIdx.x >> 5);
@@ -121,71 +123,83 @@ __global__ void __launch_bounds__(256) finish_pooled_kernel(const FinishParams p
     const int per_img = p.pool_h * p.pool_w;
     for (long long pos0 = warp0 * U; pos0 < total_pos; pos0 += nwarps * U) {
         float4 va[U], vb[U], wa[U], wb[U];
-        long long img_u[U];
-        int y_u[U], x_u[U];
+        long long orow[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             const long long pos = pos0 + u;
             wa[u] = wb[u] = make_float4(0.f, 0.f, 0.f, 0.f);
             if (pos < total_pos) {
-                img_u[u] = pos / per_img;
-                const int rem = (int)(pos - img_u[u] * per_img);
-                y_u[u] = rem / p.pool_w;
-                x_u[u] = rem - y_u[u] * p.pool_w;
-                const float4* src = reinterpret_cast<const float4*>(p.pooled + pos * 256 + lane * 8);
-                va[u] = __ldcs(src);
-                vb[u] = __ldcs(src + 1);
-                if (pool_crosses(img_u[u], y_u[u], x_u[u], p.in_pos_per_img, p.in_grid_w)) {
-                    const float4* src2 = reinterpret_cast<const float4*>(p.pooled2 + pos * 256 + lane * 8);
-                    wa[u] = __ldcs(src2);
-                    wb[u] = __ldcs(src2 + 1);
+                const long long img = pos / per_img;
+                const int rem = (int)(pos - img * per_img);
+                const int y = rem / p.pool_w, x = rem - y * p.pool_w;
+                orow[u] = img * p.out_pos_per_img + (long long)y * p.out_grid_w + x;
+                const float* src = p.pooled + pos * 256 + lane * 4;
+                va[u] = __ldcs(reinterpret_cast<const float4*>(src));
+                vb[u] = __ldcs(reinterpret_cast<const float4*>(src + 128));
+                if (pool_crosses(img, y, x, p.in_pos_per_img, p.in_grid_w)) {
+                    const float* src2 = p.pooled2 + pos * 256 + lane * 4;
+                    wa[u] = __ldcs(reinterpret_cast<const float4*>(src2));
+                    wb[u] = __ldcs(reinterpret_cast<const float4*>(src2 + 128));
                 }
             }
         }
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-            const long long pos = pos0 + u;
-            if (pos >= total_pos) break;                  // warp-uniform
-            const long long img = img_u[u];
-            const int y = y_u[u], x = x_u[u];
+            if (pos0 + u >= total_pos) break;             // warp-uniform
             // values are >= 0 (post-ReLU), and a missing second part reads as 0
-            const float m[8] = {fmaxf(va[u].x, wa[u].x), fmaxf(va[u].y, wa[u].y), fmaxf(va[u].z, wa[u].z),
-                                fmaxf(va[u].w, wa[u].w), fmaxf(vb[u].x, wb[u].x), fmaxf(vb[u].y, wb[u].y),
-                                fmaxf(vb[u].z, wb[u].z), fmaxf(vb[u].w, wb[u].w)};
-            float out[8];
+            const float ma[4] = {fmaxf(va[u].x, wa[u].x), fmaxf(va[u].y, wa[u].y), fmaxf(va[u].z, wa[u].z),
+                                 fmaxf(va[u].w, wa[u].w)};
+            const float mb[4] = {fmaxf(vb[u].x, wb[u].x), fmaxf(vb[u].y, wb[u].y), fmaxf(vb[u].z, wb[u].z),
+                                 fmaxf(vb[u].w, wb[u].w)};
+            float oa[4], ob[4];
             if (LRN) {
-                float sq[12];
+                // squares of channels c-2 .. c+2: [0,1] from the lane below, [6,7] from the lane above;
+                // channels 126..129 cross from the first block of lane 31 to the second block of lane 0
+                float qa[8], qb[8];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) sq[j + 2] = m[j] * m[j];
-                const float l0 = __shfl_up_sync(0xffffffffu, sq[8], 1);        // lane-1's channel 6
-                const float l1 = __shfl_up_sync(0xffffffffu, sq[9], 1);        // lane-1's channel 7
-                const float r0 = __shfl_down_sync(0xffffffffu, sq[2], 1);      // lane+1's channel 0
-                const float r1 = __shfl_down_sync(0xffffffffu, sq[3], 1);      // lane+1's channel 1
-                sq[0] = lane > 0 ? l0 : 0.f;
-                sq[1] = lane > 0 ? l1 : 0.f;
-                sq[10] = lane < 31 ? r0 : 0.f;
-                sq[11] = lane < 31 ? r1 : 0.f;
+                for (int j = 0; j < 4; ++j) { qa[j + 2] = ma[j] * ma[j]; qb[j + 2] = mb[j] * mb[j]; }
+                const float ua0 = __shfl_up_sync(0xffffffffu, qa[4], 1), ua1 = __shfl_up_sync(0xffffffffu, qa[5], 1);
+                const float ub0 = __shfl_up_sync(0xffffffffu, qb[4], 1), ub1 = __shfl_up_sync(0xffffffffu, qb[5], 1);
+                const float da0 = __shfl_down_sync(0xffffffffu, qa[2], 1), da1 = __shfl_down_sync(0xffffffffu, qa[3], 1);
+                const float db0 = __shfl_down_sync(0xffffffffu, qb[2], 1), db1 = __shfl_down_sync(0xffffffffu, qb[3], 1);
+                const float lo0 = __shfl_sync(0xffffffffu, qa[4], 31), lo1 = __shfl_sync(0xffffffffu, qa[5], 31);
+                const float hi0 = __shfl_sync(0xffffffffu, qb[2], 0), hi1 = __shfl_sync(0xffffffffu, qb[3], 0);
+                qa[0] = lane > 0 ? ua0 : 0.f;   qa[1] = lane > 0 ? ua1 : 0.f;
+                qa[6] = lane < 31 ? da0 : hi0;  qa[7] = lane < 31 ? da1 : hi1;
+                qb[0] = lane > 0 ? ub0 : lo0;   qb[1] = lane > 0 ? ub1 : lo1;
+                qb[6] = lane < 31 ? db0 : 0.f;  qb[7] = lane < 31 ? db1 : 0.f;
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const float s5 = sq[j] + sq[j + 1] + sq[j + 2] + sq[j + 3] + sq[j + 4];
-                    out[j] = m[j] * pow_m075(1.0f + 2e-5f * s5);
+                for (int j = 0; j < 4; ++j) {
+                    const float sa = qa[j] + qa[j + 1] + qa[j + 2] + qa[j + 3] + qa[j + 4];
+                    const float sb = qb[j] + qb[j + 1] + qb[j + 2] + qb[j + 3] + qb[j + 4];
+                    oa[j] = ma[j] * pow_m075(1.0f + 2e-5f * sa);
+                    ob[j] = mb[j] * pow_m075(1.0f + 2e-5f * sb);
                 }
             } else {
 #pragma unroll
-                for (int j = 0; j < 8; ++j) out[j] = m[j];
+                for (int j = 0; j < 4; ++j) { oa[j] = ma[j]; ob[j] = mb[j]; }
             }
-            const long long o = (img * p.out_pos_per_img + (long long)y * p.out_grid_w + x) * p.out_ld + lane * 8;
-            uint32_t ph[4], pl[4];
+            auto split4 = [](const float (&v)[4], uint2& hi, uint2& lo) {
+                uint32_t ph[2], pl[2];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const __half h0 = __float2half_rn(out[2 * j]), h1 = __float2half_rn(out[2 * j + 1]);
-                const __half e0 = __float2half_rn(out[2 * j] - __half2float(h0));
-                const __half e1 = __float2half_rn(out[2 * j + 1] - __half2float(h1));
-                ph[j] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
-                pl[j] = (uint32_t)__half_as_ushort(e0) | ((uint32_t)__half_as_ushort(e1) << 16);
-            }
-            *reinterpret_cast<uint4*>(p.out_hi + o) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
-            *reinterpret_cast<uint4*>(p.out_lo + o) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+                for (int j = 0; j < 2; ++j) {
+                    const __half h0 = __float2half_rn(v[2 * j]), h1 = __float2half_rn(v[2 * j + 1]);
+                    const __half e0 = __float2half_rn(v[2 * j] - __half2float(h0));
+                    const __half e1 = __float2half_rn(v[2 * j + 1] - __half2float(h1));
+                    ph[j] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
+                    pl[j] = (uint32_t)__half_as_ushort(e0) | ((uint32_t)__half_as_ushort(e1) << 16);
+                }
+                hi = make_uint2(ph[0], ph[1]);
+                lo = make_uint2(pl[0], pl[1]);
+            };
+            uint2 ha, la, hb, lb;
+            split4(oa, ha, la);
+            split4(ob, hb, lb);
+            const long long o = orow[u] * p.out_ld + lane * 4;
+            *reinterpret_cast<uint2*>(p.out_hi + o) = ha;
+            *reinterpret_cast<uint2*>(p.out_hi + o + 128) = hb;
+            *reinterpret_cast<uint2*>(p.out_lo + o) = la;
+            *reinterpret_cast<uint2*>(p.out_lo + o + 128) = lb;
         }
     }
 }
@@ -359,8 +373,8 @@ int launch_finish_pooled(const FinishParams& p, long long n_img, int num_sms, cu
     const long long total = n_img * p.pool_h * p.pool_w;
     if (total <= 0) return 0;
     if (p.out_ld % 8 != 0) return fail(-1, "finish_pooled: output rows must be 16-byte aligned");
-    long long blocks = (long long)num_sms * 6;           // CTAs resident per SM at ~40 registers
-    if (blocks > (total + 31) / 32) blocks = (total + 31) / 32;
+    long long blocks = (long long)num_sms * 8;
+    if (blocks > (total + 15) / 16) blocks = (total + 15) / 16;
     if (p.lrn) finish_pooled_kernel<true><<<(unsigned)blocks, 256, 0, stream>>>(p, total);
     else       finish_pooled_kernel<false><<<(unsigned)blocks, 256, 0, stream>>>(p, total);
     SVX_LAUNCH_CHECK("finish_pooled_kernel");

@@ -460,6 +460,15 @@ int run_cnn(svx_handle* h, long long n, int32_t* labels, float* probs, float* lo
     return 0;
 }
 
+// Micro-batch size for a call of n sites: the fewest passes that fit the workspaces, of equal size
+// (12 500 sites with room for 10 000 run as 2 x 6 250, not 10 000 + 2 500: the fc layers' tile waves
+// and every kernel's tail are paid per pass)
+long long balanced_batch(long long n, long long max_batch) {
+    if (n <= max_batch) return n > 0 ? n : 1;
+    const long long passes = (n + max_batch - 1) / max_batch;
+    return (n + passes - 1) / passes;
+}
+
 // rows -> conv2 operand: the fused sparse front end (encode + conv1 + ReLU + pool1 + LRN1)
 int encode_front(svx_handle* h, const int32_t* rows_dev, long long m, cudaStream_t st) {
     FrontParams fp{h->front_w255, h->front_base, h->x2_hi, h->x2_lo, h->front_scratch, h->front_blocks,
@@ -619,8 +628,9 @@ int svx_classify_device(svx_handle* h, const int32_t* rows_dev, int64_t n, int32
     DeviceGuard guard(h->device);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     SVX_CUDA_CHECK(cudaStreamWaitEvent(st, h->busy, 0));
-    for (int64_t s = 0; s < n; s += h->max_batch) {
-        const int64_t m = n - s < h->max_batch ? n - s : h->max_batch;
+    const int64_t mb = balanced_batch(n, h->max_batch);
+    for (int64_t s = 0; s < n; s += mb) {
+        const int64_t m = n - s < mb ? n - s : mb;
         int rc;
         if ((rc = encode_front(h, rows_dev + s * SVX_ROW_FIELDS, m, st))) return rc;
         if ((rc = run_cnn(h, m, labels_dev + s, probs_dev + s * SVX_NUM_CLASSES,
@@ -639,8 +649,9 @@ int svx_classify(svx_handle* h, const int32_t* rows_host, int64_t n, int32_t* la
     DeviceGuard guard(h->device);
     cudaStream_t st = h->stream;
     SVX_CUDA_CHECK(cudaStreamWaitEvent(st, h->busy, 0));
-    for (int64_t s = 0; s < n; s += h->max_batch) {
-        const int64_t m = n - s < h->max_batch ? n - s : h->max_batch;
+    const int64_t mb = balanced_batch(n, h->max_batch);
+    for (int64_t s = 0; s < n; s += mb) {
+        const int64_t m = n - s < mb ? n - s : mb;
         int rc;
         SVX_CUDA_CHECK(cudaMemcpyAsync(h->rows_dev, rows_host + s * SVX_ROW_FIELDS,
                                        (size_t)m * SVX_ROW_FIELDS * sizeof(int32_t), cudaMemcpyHostToDevice, st));
@@ -664,8 +675,9 @@ int svx_classify_device_calls(svx_handle* h, const int32_t* rows_dev, int64_t n,
     DeviceGuard guard(h->device);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     SVX_CUDA_CHECK(cudaStreamWaitEvent(st, h->busy, 0));
-    for (int64_t s = 0; s < n; s += h->max_batch) {
-        const int64_t m = n - s < h->max_batch ? n - s : h->max_batch;
+    const int64_t mb = balanced_batch(n, h->max_batch);
+    for (int64_t s = 0; s < n; s += mb) {
+        const int64_t m = n - s < mb ? n - s : mb;
         int rc;
         CallSinks sinks = {};
         sinks.count = 1;
@@ -757,8 +769,9 @@ int svx_classify_exchange(svx_handle* h, svx_exchange* x, const int32_t* rows_de
     SVX_CUDA_CHECK(cudaStreamWaitEvent(st, h->busy, 0));
     const unsigned long long epoch = ++x->epoch;
     const int parity = (int)(epoch & 1ull);
-    for (int64_t s = 0; s < n; s += h->max_batch) {
-        const int64_t m = n - s < h->max_batch ? n - s : h->max_batch;
+    const int64_t mb = balanced_batch(n, h->max_batch);
+    for (int64_t s = 0; s < n; s += mb) {
+        const int64_t m = n - s < mb ? n - s : mb;
         int rc;
         CallSinks sinks = {};
         sinks.count = x->world;

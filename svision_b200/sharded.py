@@ -146,7 +146,9 @@ class Exchange:
     def classify(self, rows_dev: torch.Tensor):
         """rows of this rank's shard (cuda int32 [n<=per,12]) -> (labels int32[world*per], scores
         float32[world*per]) in rank-major (= file) order: zero-copy views of the gathered buffer,
-        valid after the current stream's work and until the next-but-one call."""
+        valid after the current stream's work and until the next-but-one call.  Asynchronous: a rank
+        that never delivers is detected by the wait kernel's timeout, see :meth:`status` /
+        :meth:`result`."""
         clf = self.clf
         assert rows_dev.dtype == torch.int32 and rows_dev.is_contiguous() and rows_dev.device == clf.torch_device
         ptr = ctypes.c_void_p()
@@ -157,8 +159,19 @@ class Exchange:
         return calls[:, 0], calls[:, 1].view(torch.float32)
 
     def status(self) -> None:
-        """Synchronises and raises if a rank failed to show up within the timeout."""
+        """Synchronises the device and raises if a rank failed to show up within the timeout
+        (``SVX_EXCHANGE_TIMEOUT_MS``, default 30 s).  Until it is called, the error stays set and every
+        further :meth:`classify` raises; the late rank's calls in the gathered buffer of the call
+        that timed out are poisoned (label -1, score NaN)."""
         self._check(self._lib.svx_exchange_status(self._x), "svx_exchange_status")
+
+    def result(self, rows_dev: torch.Tensor):
+        """:meth:`classify` + :meth:`status`: the gathered (labels, scores), guaranteed complete (raises
+        if any rank did not deliver).  Synchronises; use :meth:`classify` to keep the stream asynchronous
+        and call :meth:`status` before trusting what was gathered."""
+        out = self.classify(rows_dev)
+        self.status()
+        return out
 
     def close(self) -> None:
         if getattr(self, "_x", None):

@@ -154,23 +154,3 @@ def test_config1_demo_bed_through_step2_on_the_gpu(clf, synthetic_weights, tmp_p
         assert fa[:5] == fb[:5] and fa[6:] == fb[6:] and abs(float(fa[5]) - float(fb[5])) <= 2
     assert [l for l in got if l.startswith("#")] == [l for l in ref if l.startswith("#")]
     assert len(got) == len(ref)
-
-
-def test_fused_exchange_two_gpus_when_available():
-    """On a box with at least two GPUs: tools/exchange_check.py under torchrun (fused exchange ==
-    NCCL all-gather == single-GPU result, bit for bit).  Skipped on single-GPU boxes; the recorded runs
-    on 2 and 8 GPUs are in profiles/."""
-    import json
-    import subprocess
-    import sys
-    if torch.cuda.device_count() < 2:
-        pytest.skip("needs two GPUs")
-    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
-           "--master-addr", "127.0.0.1", "--master-port", "29533", os.path.join(root, "tools", "exchange_check.py"),
-           "--sites", "3000", "--iters", "3"]
-    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
-    assert out.returncode == 0, out.stderr[-2000:]
-    line = [l for l in out.stdout.splitlines() if l.startswith("{")][-1]
-    res = json.loads(line)
-    assert res["world"] == 2 and res["all_paths_bit_identical"] is True

@@ -28,7 +28,12 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--sites", type=int, default=10_000, help="sites per rank")
     ap.add_argument("--iters", type=int, default=20)
+    ap.add_argument("--timeout-test", action="store_true",
+                    help="the last rank shows up late once: the others must see the timeout (sticky error, "
+                         "poisoned calls), not stale results")
     a = ap.parse_args()
+    if a.timeout_test:
+        os.environ["SVX_EXCHANGE_TIMEOUT_MS"] = "400"
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     local = int(os.environ.get("LOCAL_RANK", rank))
     torch.cuda.set_device(local)
@@ -59,6 +64,45 @@ def main():
         l_1, s_1 = clf.classify_device_calls(clf.rows_to_device(rows))
         ok &= bool(torch.equal(l_1, l_f[:n_total])) and bool(torch.equal(s_1, s_f[:n_total]))
 
+    timeout_ok = None
+    if a.timeout_test:
+        import time
+        from svision_b200 import _lib
+        dist.barrier()
+        torch.cuda.synchronize()
+        late = world - 1
+        if rank == late:
+            time.sleep(2.5)                               # > SVX_EXCHANGE_TIMEOUT_MS
+        l_t, s_t = x.classify(mine)
+        torch.cuda.synchronize()
+        if rank == late:
+            timeout_ok = True                             # its own wait saw everybody (they came first)
+            try:
+                x.status()
+            except _lib.SvxError:
+                timeout_ok = False
+        else:
+            seen, sticky = False, False
+            try:
+                x.classify(mine)                          # the error is sticky: refused before any launch
+            except _lib.SvxError:
+                sticky = True
+            try:
+                x.status()
+            except _lib.SvxError as e:
+                seen = f"rank {late}" in str(e)
+            region = l_t[late * per:(late + 1) * per]
+            poisoned = bool((region == -1).all().item())
+            own = bool(torch.equal(l_t[rank * per:(rank + 1) * per], l_n[rank * per:(rank + 1) * per]))
+            timeout_ok = seen and sticky and poisoned and own
+        dist.barrier()
+        # after status() the exchange works again: the refused call did not consume an epoch, so the
+        # ranks are still aligned
+        l_n, s_n = via_nccl()
+        l_f, s_f = x.result(mine)
+        timeout_ok = timeout_ok and bool(torch.equal(l_n, l_f)) and bool(torch.equal(s_n, s_f))
+        ok &= timeout_ok
+
     def timed(fn):
         for _ in range(3):
             fn()
@@ -82,6 +126,8 @@ def main():
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0:
         print(json.dumps({"world": world, "sites_per_rank": per, "all_paths_bit_identical": bool(flag.item()),
+                          "timeout_test": "detected, poisoned, recovered on every rank" if a.timeout_test and flag.item()
+                          else ("FAILED" if a.timeout_test else "not run"),
                           "ms_per_step_nccl_allgather": ms_nccl, "ms_per_step_fused_exchange": ms_fused,
                           "sites_per_s_nccl": world * per / ms_nccl * 1e3,
                           "sites_per_s_fused": world * per / ms_fused * 1e3}), flush=True)

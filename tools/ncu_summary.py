@@ -1,7 +1,7 @@
 """Summaries of ncu output for profiles/ (run in the build container; ncu reads reports without a GPU).
 
     python tools/ncu_summary.py launches gpurun_out/x/ncu_launches.csv        # per-kernel time shares
-    python tools/ncu_summary.py full gpurun_out/x/full_conv.ncu-rep [...]     # one line per profiled launch
+    python tools/ncu_summary.py full [--sites=N] gpurun_out/x/full_conv.ncu-rep [...]   # one line per profiled launch
 
 `full` reads `ncu -i REPORT --page raw --csv` and prints duration, tensor-pipe activity, SM / L2 / L1 / DRAM
 throughput (% of peak), DRAM bytes read / written per launch (the roofline "traffic"), registers, SM clock."""
@@ -38,6 +38,10 @@ def short(name: str) -> str:
 
 
 def full(paths):
+    sites = [p.split("=", 1)[1] for p in paths if p.startswith("--sites=")]
+    paths = [p for p in paths if not p.startswith("--sites=")]
+    if sites:
+        print(f"# sites per launch: {int(sites[0])}   (bench.py reads this line for roofline.traffic)")
     print("# ncu --set full --clock-control none --import-source on (per profiled launch); dramR/dramW = "
           "dram__bytes_read/write.sum per launch (the roofline \"traffic\")")
     print(f"{'kernel':46s}{'grid':>8s}" + "".join(f"{k:>12s}" for k in METRICS))
