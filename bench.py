@@ -699,8 +699,10 @@ def run_strong(args, clf, sharded, sites, dist, world, rank, dev, k_rows, k_labe
     torch.cuda.synchronize()
     if x is not None:
         x.status()
+    l_host, s_host = l.cpu().numpy(), s.cpu().numpy()    # views of the exchange's buffer: copy before closing it
+    if x is not None:
         x.close()
-    ok, err = check_known(l.cpu().numpy(), s.cpu().numpy(), world, per, k_labels, k_scores)
+    ok, err = check_known(l_host, s_host, world, per, k_labels, k_scores)
     per_rank = all_ranks({"rank": rank, "ms_per_step": my_ms})
     oks = all_ranks(ok)
     return {"workload": "configs[2]: synthetic 100k candidate sites, HiFi profile (set P1, seed 20261018), "

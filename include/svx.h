@@ -143,7 +143,7 @@ void svx_multi_destroy(svx_multi *m);
  * is the per-site call.  svx_classify_exchange classifies this rank's shard and its fc8 kernel stores
  * every call straight into the gathered buffer of EVERY rank (peer-mapped over NVLink via CUDA IPC)
  * and publishes an epoch flag; a one-warp kernel then waits for the other ranks' flags.  No separate
- * collective runs.  Setup: every rank creates an exchange, exports its 64-byte IPC handle, the
+ * collective runs.  Setup: every rank creates an exchange, exports its IPC handle blob, the
  * handles are all-gathered by the caller (torch.distributed in svision_b200/sharded.py) and attached.
  *   gathered_dev  device pointer to svx_call[world][sites_per_rank] (rank-major = file order for
  *                 contiguous shards), valid once the work queued on `stream` has finished and until
@@ -155,11 +155,11 @@ void svx_multi_destroy(svx_multi *m);
  * buffer (label -1, score NaN -- stale results of an earlier epoch can not be mistaken for this one's)
  * and raises a sticky error word in mapped host memory.  The error is returned by svx_exchange_status
  * (which synchronises the device and clears it) and by every later svx_classify_exchange until then. */
-#define SVX_IPC_HANDLE_BYTES 64
+#define SVX_IPC_HANDLE_BYTES 72   /* CUDA IPC handle (64) + offset of the buffer inside the exported allocation */
 typedef struct svx_exchange svx_exchange;
 int svx_exchange_create(svx_handle *h, int rank, int world, int64_t sites_per_rank, svx_exchange **out);
-int svx_exchange_export(svx_exchange *x, void *ipc_handle_out /* 64 bytes */);
-int svx_exchange_attach(svx_exchange *x, const void *ipc_handles /* [world][64], rank order */);
+int svx_exchange_export(svx_exchange *x, void *ipc_handle_out /* SVX_IPC_HANDLE_BYTES */);
+int svx_exchange_attach(svx_exchange *x, const void *ipc_handles /* [world][SVX_IPC_HANDLE_BYTES], rank order */);
 int svx_classify_exchange(svx_handle *h, svx_exchange *x, const int32_t *rows_dev, int64_t n,
                           const svx_call **gathered_dev, void *stream);
 int svx_exchange_status(svx_exchange *x);

@@ -24,7 +24,7 @@ SYMBOLS = (
     "svx_multi_create", "svx_multi_classify", "svx_multi_device_count", "svx_multi_last_split",
     "svx_multi_destroy",
 )
-IPC_HANDLE_BYTES = 64
+IPC_HANDLE_BYTES = 72
 
 
 class SvxWeights(ctypes.Structure):

@@ -127,6 +127,7 @@ struct svx_exchange {
     long long per_rank = 0;
     void* local = nullptr;                          // cudaMalloc: [flags 256 B][region 0][region 1]
     void* base[CALL_MAX_SINKS] = {};                // base[r]: rank r's buffer as mapped here
+    void* mapped[CALL_MAX_SINKS] = {};              // what cudaIpcOpenMemHandle returned (to close)
     bool opened[CALL_MAX_SINKS] = {};
     bool attached = false;
     unsigned int* done = nullptr;                   // fc8 CTA counter
@@ -725,13 +726,28 @@ int svx_exchange_create(svx_handle* h, int rank, int world, int64_t sites_per_ra
     return SVX_OK;
 }
 
+// A CUDA IPC handle names the whole driver allocation a pointer lives in (cudaMalloc sub-allocates
+// small requests from larger blocks), and opening it yields that allocation's BASE: the exported blob
+// therefore carries the buffer's offset from the base as well.
 int svx_exchange_export(svx_exchange* x, void* ipc_handle_out) {
     if (!x || !ipc_handle_out) return fail(SVX_ERR_INVALID, "svx_exchange_export: bad arguments");
-    static_assert(sizeof(cudaIpcMemHandle_t) == SVX_IPC_HANDLE_BYTES, "IPC handle size");
+    static_assert(sizeof(cudaIpcMemHandle_t) + sizeof(uint64_t) == SVX_IPC_HANDLE_BYTES, "IPC blob size");
     DeviceGuard guard(x->device);
     cudaIpcMemHandle_t hd;
     SVX_CUDA_CHECK(cudaIpcGetMemHandle(&hd, x->local));
+    typedef CUresult (*PFN_range)(CUdeviceptr*, size_t*, CUdeviceptr);
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuMemGetAddressRange", &fn, cudaEnableDefault, &qres) != cudaSuccess ||
+        qres != cudaDriverEntryPointSuccess || !fn)
+        return fail(SVX_ERR_CUDA, "svx_exchange_export: cuMemGetAddressRange entry point not available");
+    CUdeviceptr base = 0;
+    size_t size = 0;
+    if (reinterpret_cast<PFN_range>(fn)(&base, &size, reinterpret_cast<CUdeviceptr>(x->local)) != CUDA_SUCCESS)
+        return fail(SVX_ERR_CUDA, "svx_exchange_export: cuMemGetAddressRange failed");
+    const uint64_t offset = reinterpret_cast<CUdeviceptr>(x->local) - base;
     std::memcpy(ipc_handle_out, &hd, sizeof(hd));
+    std::memcpy(static_cast<char*>(ipc_handle_out) + sizeof(hd), &offset, sizeof(offset));
     return SVX_OK;
 }
 
@@ -742,11 +758,15 @@ int svx_exchange_attach(svx_exchange* x, const void* ipc_handles) {
     for (int r = 0; r < x->world; ++r) {
         if (r == x->rank) continue;
         cudaIpcMemHandle_t hd;
-        std::memcpy(&hd, static_cast<const char*>(ipc_handles) + (size_t)r * SVX_IPC_HANDLE_BYTES, sizeof(hd));
-        cudaError_t e = cudaIpcOpenMemHandle(&x->base[r], hd, cudaIpcMemLazyEnablePeerAccess);
+        uint64_t offset = 0;
+        const char* blob = static_cast<const char*>(ipc_handles) + (size_t)r * SVX_IPC_HANDLE_BYTES;
+        std::memcpy(&hd, blob, sizeof(hd));
+        std::memcpy(&offset, blob + sizeof(hd), sizeof(offset));
+        cudaError_t e = cudaIpcOpenMemHandle(&x->mapped[r], hd, cudaIpcMemLazyEnablePeerAccess);
         if (e != cudaSuccess)
             return fail(SVX_ERR_CUDA, "svx_exchange_attach: cudaIpcOpenMemHandle(rank " + std::to_string(r) +
                                           "): " + cudaGetErrorString(e));
+        x->base[r] = static_cast<char*>(x->mapped[r]) + offset;
         x->opened[r] = true;
     }
     x->attached = true;
@@ -812,7 +832,7 @@ void svx_exchange_destroy(svx_exchange* x) {
     DeviceGuard guard(x->device);
     cudaDeviceSynchronize();
     for (int r = 0; r < x->world; ++r)
-        if (x->opened[r]) cudaIpcCloseMemHandle(x->base[r]);
+        if (x->opened[r]) cudaIpcCloseMemHandle(x->mapped[r]);
     cudaFree(x->local);
     cudaFree(x->done);
     if (x->error_host) cudaFreeHost(x->error_host);

@@ -90,7 +90,7 @@ class Exchange:
     every rank stores its per-site ``(label, score)`` calls straight into the gathered buffer of
     EVERY rank over NVLink and publishes a flag; no collective kernel runs on the path.
 
-    ``torch.distributed`` is used once, at construction, to all-gather the 64-byte CUDA IPC handles.
+    ``torch.distributed`` is used once, at construction, to all-gather the CUDA IPC handle blobs.
     Every rank must call :meth:`classify` the same number of times, with at most ``sites_per_rank``
     rows (use :func:`shard_rows`)."""
 
