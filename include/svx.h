@@ -222,6 +222,10 @@ void svx_launch_count_reset(void);
 #define SVX_BED_FLAG_FORWARD 2      /* column 20 == "True" (predict.py:229) */
 #define SVX_BED_FLAG_UNCOVERED 4    /* column 16 == "sigUncovered" (output.py:526) */
 #define SVX_BED_FLAG_SAME_REGION 8  /* column 0 equals the previous row's (predict.py:235) */
+#define SVX_BED_FLAG_COMPLEMENT 16  /* one of the label columns (0, 13, 15, 16, 19, 20, 21) contains the
+                                       substring "complement": the reference skips the row whatever else
+                                       it holds (predict.py:214 tests the joined label; its own pad rows
+                                       are labelled 'complement-complement', create_batch.py:56) */
 int svx_bed_count_rows(const char *text, int64_t len, int64_t *n_rows);
 int svx_bed_parse(const char *text, int64_t len, int64_t n_rows, int32_t *rows, int64_t *bkp,
                   int64_t *spans, int32_t *flags);

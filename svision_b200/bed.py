@@ -23,7 +23,7 @@ import numpy as np
 from . import _lib
 
 N_COLS = 23
-FLAG_MAIN, FLAG_FORWARD, FLAG_UNCOVERED, FLAG_SAME_REGION = 1, 2, 4, 8     # include/svx.h
+FLAG_MAIN, FLAG_FORWARD, FLAG_UNCOVERED, FLAG_SAME_REGION, FLAG_COMPLEMENT = 1, 2, 4, 8, 16     # include/svx.h
 _SPAN_OF = {"region": 0, "read_num": 1, "read_name": 2, "sig_type": 3, "sig_score": 4, "forward": 5,
             "mechanism": 6}
 
@@ -56,6 +56,12 @@ class SegmentsTable:
             fl |= (self.forward == "True").astype(np.int32) * FLAG_FORWARD
             fl |= (self.sig_type == "sigUncovered").astype(np.int32) * FLAG_UNCOVERED
             fl[1:] |= (self.region[1:] == self.region[:-1]).astype(np.int32) * FLAG_SAME_REGION
+            # predict.py:214 skips a row when its joined label contains 'complement' anywhere
+            comp = np.zeros(n, dtype=bool)
+            for col in (self.region, self.read_num, self.read_name, self.sig_type, self.sig_score,
+                        self.forward, self.mechanism):
+                comp |= np.char.find(np.asarray(col, dtype=str), "complement") >= 0
+            fl |= comp.astype(np.int32) * FLAG_COMPLEMENT
         return fl
 
     def __len__(self) -> int:

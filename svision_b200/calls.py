@@ -339,8 +339,9 @@ def call_chromosome(table, labels: np.ndarray, probs: np.ndarray, options, genot
     """The per-row loop of ``Predict.run`` (predict.py:213-300) followed, region by region, by
     aggregation and record assembly.  Returns ``[(qual, vcf_line), ...]`` in file order.
 
-    Row rules kept from the reference: a forward signature classified INV is dropped before it can
-    open a region (predict.py:229-231); a region is flushed when the *next kept* row names another
+    Row rules kept from the reference: a row whose label columns contain ``complement`` is skipped
+    (predict.py:214); a forward signature classified INV is dropped before it can open a region
+    (predict.py:229-231); a region is flushed when the *next kept* row names another
     region (predict.py:235-247); a row of a non-main segment pair (id without ``m``) classified DEL
     or INS still contributes its score and metadata but no call (predict.py:279-281); later rows
     overwrite earlier ones with the same read id and class."""
@@ -354,7 +355,7 @@ def call_chromosome(table, labels: np.ndarray, probs: np.ndarray, options, genot
         if records is not None:
             return _genotyped(records, genotype, options)
     pred = pred_arr.tolist()
-    fwd_inv = ((table.forward == "True") & (pred_arr == 2)).tolist() if n else []
+    fwd_inv = (((table.forward == "True") & (pred_arr == 2)) | ((np.asarray(table.flags) & 16) != 0)).tolist() if n else []
     read_num, region_col, read_name = table.read_num.tolist(), table.region.tolist(), table.read_name.tolist()
     sig_type, sig_score, mech = table.sig_type.tolist(), table.sig_score.tolist(), table.mechanism.tolist()
     b0, b1, b2 = table.bkp_start.tolist(), table.bkp_end.tolist(), table.bkp_len.tolist()
@@ -409,9 +410,9 @@ def _genotyped(records: list, genotype, options) -> List[Tuple[object, str]]:
 
 
 def region_cuts(table, chunk_rows: int) -> List[int]:
-    """Chunk boundaries ``[0, c1, ..., N]``: about ``chunk_rows`` rows each, cut only where the region
-    column changes (a region is flushed when the next row names another one, predict.py:235-247, so
-    whole chromosomes may be processed chunk by chunk)."""
+    """Chunk boundaries ``[0, c1, ..., N]``: about ``chunk_rows`` rows each, cut where the region column
+    changes (so that little is held back at a seam; exactness does not depend on it, see
+    :func:`call_chromosome_streamed`)."""
     n = len(table)
     if n == 0:
         return [0]
@@ -434,12 +435,30 @@ def region_cuts(table, chunk_rows: int) -> List[int]:
     return cuts
 
 
+def _open_region_start(table, labels: np.ndarray) -> int:
+    """First row of the region that is still OPEN at the end of ``table``: the earliest kept row of the
+    trailing run of kept rows naming one region (dropped rows in between do not close it,
+    predict.py:214,229-247).  ``len(table)`` if no row is kept."""
+    flags = np.asarray(table.flags)
+    kept = np.flatnonzero(~((((flags & 2) != 0) & (np.asarray(labels) == 2)) | ((flags & 16) != 0)))
+    if kept.size == 0:
+        return len(table)
+    region = table.region
+    last = region[kept[-1]]
+    j = kept.size - 1
+    while j > 0 and region[kept[j - 1]] == last:
+        j -= 1
+    return int(kept[j])
+
+
 def call_chromosome_streamed(table, classify: Callable, options, genotype, chunk_rows: int = 65536,
                              aggregate: Callable = aggregate_region) -> List[Tuple[object, str]]:
     """:func:`call_chromosome` with the GPU and the host working at the same time: ``classify(rows) ->
     (labels, probs)`` of chunk k+1 runs on a worker thread (``svx_classify`` releases the GIL) while
-    this thread turns chunk k into records.  Chunks end where the region changes, so the records are
-    exactly those of one ``call_chromosome`` over the whole table."""
+    this thread turns chunk k into records.  The reference closes a region only when the next KEPT row
+    names another one, and which rows are kept depends on the labels: the region still open at the end
+    of a chunk is therefore held back and processed with the next chunk, so the records are exactly
+    those of one ``call_chromosome`` over the whole table wherever the cuts fall."""
     from concurrent.futures import ThreadPoolExecutor
     cuts = region_cuts(table, max(int(chunk_rows), 1))
     spans = list(zip(cuts[:-1], cuts[1:]))
@@ -447,6 +466,9 @@ def call_chromosome_streamed(table, classify: Callable, options, genotype, chunk
         labels, probs = classify(table.rows)
         return call_chromosome(table, labels, probs, options, genotype, aggregate)
     records: list = []
+    start = 0                                    # rows [start, a) of earlier chunks are still pending
+    held_l = np.zeros(0, np.int32)
+    held_p = np.zeros((0, 5), np.float32)
     with ThreadPoolExecutor(max_workers=1) as pool:
         pending = pool.submit(classify, np.ascontiguousarray(table.rows[spans[0][0]:spans[0][1]]))
         for k, (a, b) in enumerate(spans):
@@ -454,7 +476,15 @@ def call_chromosome_streamed(table, classify: Callable, options, genotype, chunk
             if k + 1 < len(spans):
                 na, nb = spans[k + 1]
                 pending = pool.submit(classify, np.ascontiguousarray(table.rows[na:nb]))
-            records.extend(call_chromosome(table.take(slice(a, b)), labels, probs, options, genotype, aggregate))
+            labels = np.concatenate([held_l, np.asarray(labels)])
+            probs = np.concatenate([held_p, np.asarray(probs)])
+            sub = table.take(slice(start, b))
+            cut = len(sub) if k + 1 == len(spans) else _open_region_start(sub, labels)
+            if cut > 0:
+                records.extend(call_chromosome(sub.take(slice(0, cut)) if cut < len(sub) else sub,
+                                               labels[:cut], probs[:cut], options, genotype, aggregate))
+            held_l, held_p = labels[cut:], probs[cut:]
+            start += cut
     return records
 
 

@@ -10,6 +10,7 @@
 //   0 region | 1-5 seg1 xS xE yS yE fwd | 6-10 seg2 | 11 read_len | 12 ref_len | 13 read id |
 //   14 sub id | 15 qname | 16 sig type | 17-18 bkp start/end | 19 score | 20 forward | 21 mechanism |
 //   22 bkp len
+#include <algorithm>
 #include <cstdint>
 #include <cstring>
 #include <string>
@@ -152,6 +153,11 @@ extern "C" int svx_bed_parse(const char* text, int64_t len, int64_t n_rows, int3
         if (prev_region.p && prev_region.n == f[0].n && std::memcmp(prev_region.p, f[0].p, static_cast<size_t>(f[0].n)) == 0)
             fl |= SVX_BED_FLAG_SAME_REGION;
         prev_region = f[0];
+        for (int k = 0; k < SVX_BED_SPANS; ++k) {                        // predict.py:214
+            const Field& c = f[kSpanCols[k]];
+            static const char kWord[] = "complement";
+            if (c.n >= 10 && std::search(c.p, c.p + c.n, kWord, kWord + 10) != c.p + c.n) fl |= SVX_BED_FLAG_COMPLEMENT;
+        }
         flags[i] = fl;
         ++i;
         p = e + 1;

@@ -265,6 +265,7 @@ int svx_calls_aggregate(const char* text, int64_t len, int64_t n, const int64_t*
     for (int64_t i = 0; i < n && rc == SVX_OK; ++i) {
         const int32_t fl = flags[i];
         const int pred = labels[i];
+        if (fl & SVX_BED_FLAG_COMPLEMENT) continue;                        // predict.py:214
         if ((fl & SVX_BED_FLAG_FORWARD) && pred == 2) continue;           // predict.py:229-231
         if (region_row < 0 || !(span(i, 0) == span(region_row, 0))) {     // predict.py:235-247
             flush();

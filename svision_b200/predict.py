@@ -48,7 +48,12 @@ def replay_rows(table: "_bed.SegmentsTable", labels: np.ndarray, probs: np.ndarr
     sig_types, predict_scores = [], []
     last_region = ""
     flushed = 0
+    complement = (np.asarray(table.flags) & _bed.FLAG_COMPLEMENT) != 0
     for i in range(len(table)):
+        # a row whose label contains 'complement' anywhere is skipped outright (predict.py:214: the
+        # reference's pad rows, but also any read / contig / mechanism named like that)
+        if complement[i]:
+            continue
         read_num = str(table.read_num[i])
         region = str(table.region[i])
         pred = int(labels[i])

@@ -287,3 +287,93 @@ def test_call_chromosome_live_vs_reference(seed):
         parsed = _parsed(table, pathlib.Path(d))
         nat_vcf, nat_score = render(calls.call_chromosome(parsed, labels, probs, opt, make_table(aln)))
     assert nat_vcf == vcf and nat_score == score
+
+
+# ---- the reference's two row-skip rules at the seams (predict.py:214,229-247) -----------------------------
+def _with_strings(table, **cols):
+    """A copy of a string-column table with some columns replaced."""
+    from svision_b200 import bed
+    kw = {c: getattr(table, c).copy() for c in ("region", "read_num", "read_name", "sig_type", "sig_score",
+                                                "forward", "mechanism")}
+    kw.update(cols)
+    return bed.SegmentsTable(table.rows.copy(), table.bkp_start.copy(), table.bkp_end.copy(),
+                             table.bkp_len.copy(), **kw)
+
+
+def test_rows_labelled_complement_are_skipped_like_the_reference(golden, tmp_path):
+    """predict.py:214 skips every row whose joined label contains 'complement' -- its own pad rows, but
+    also a read or mechanism that happens to be named like that.  All routes (native aggregation over
+    the parsed text, pure Python, the replayed loop feeding the reference's own functions) must give
+    the text of the same stream WITHOUT those rows."""
+    g, table, aln = golden
+    n = 1500
+    table = table.take(slice(0, n))
+    labels, probs = g["labels"][:n], g["probs"][:n]
+    rng = np.random.default_rng(5)
+    hit = np.sort(rng.choice(n, 40, replace=False))
+    names = table.read_name.copy().astype(object)
+    mech = table.mechanism.copy().astype(object)
+    for i in hit[:20]:
+        names[i] = f"read_complement_{i}"
+    for i in hit[20:]:
+        mech[i] = "xcomplementx"
+    marked = _with_strings(table, read_name=np.array(names.tolist()), mechanism=np.array(mech.tolist()))
+    keep = np.setdiff1d(np.arange(n), hit)
+    expect = table.take(keep)
+    opt = G.options(3, True)
+    at = make_table(aln)
+    want = render(calls.call_chromosome(expect, labels[keep], probs[keep], opt, at))
+    assert (np.asarray(marked.flags)[hit] & 16).all() and not (np.asarray(marked.flags)[keep] & 16).any()
+    assert render(calls.call_chromosome(marked, labels, probs, opt, at)) == want          # Python route
+    parsed = _parsed(marked, tmp_path)                                                     # native route
+    assert (np.asarray(parsed.flags)[hit] & 16).all() and not (np.asarray(parsed.flags)[keep] & 16).any()
+    assert render(calls.call_chromosome(parsed, labels, probs, opt, at)) == want
+    assert render(calls.call_chromosome_streamed(parsed, lambda r: (labels[:0], probs[:0]) if r.shape[0] == 0 else
+                                                 _labels_for(parsed, labels, probs, r), opt, at, chunk_rows=200)) == want
+    # the replayed loop (what feeds the reference's own aggregate / write functions)
+    from svision_b200 import predict
+    seen_a, seen_b = [], []
+    predict.replay_rows(marked, labels, probs, lambda region, reads, *rest: seen_a.append((region, dict(reads), [list(map(str, r)) if isinstance(r, list) else dict(r) for r in rest])))
+    predict.replay_rows(expect, labels[keep], probs[keep], lambda region, reads, *rest: seen_b.append((region, dict(reads), [list(map(str, r)) if isinstance(r, list) else dict(r) for r in rest])))
+    assert seen_a == seen_b
+
+
+def _labels_for(table, labels, probs, rows):
+    """The labels of exactly these (contiguous) rows of `table`."""
+    n = rows.shape[0]
+    for i in np.flatnonzero((table.rows[:, :] == rows[0]).all(axis=1)):
+        if i + n <= len(table) and np.array_equal(table.rows[i:i + n], rows):
+            return labels[i:i + n], probs[i:i + n]
+    raise AssertionError("rows not found")
+
+
+def test_streamed_seams_do_not_split_a_region_whose_interruption_is_dropped(golden):
+    """Region A, then rows of region B that are ALL dropped (forward + INV, predict.py:229-231), then A
+    again: the reference never sees B, so A stays one region.  A chunk cut that lands inside or next to
+    the dropped run must not produce a second record for A."""
+    g, table, aln = golden
+    opt = G.options(1, True)
+    at = make_table(aln)
+    a = np.flatnonzero(table.region == table.region[0])
+    first_b = int(a[-1]) + 1
+    b = np.flatnonzero(table.region == table.region[first_b])
+    assert len(a) >= 4 and len(b) >= 2
+    half = len(a) // 2
+    order = np.concatenate([a[:half], b, a[half:], np.arange(int(b[-1]) + 1, int(b[-1]) + 400)])
+    t = table.take(order)
+    labels, probs = g["labels"][order].copy(), g["probs"][order].copy()
+    fwd = t.forward.copy()
+    fwd[half:half + len(b)] = "True"                     # every B row: forward ...
+    labels[half:half + len(b)] = 2                       # ... and classified INV -> dropped
+    t = _with_strings(t, forward=fwd)
+    whole = render(calls.call_chromosome(t, labels, probs, opt, at))
+    for chunk_rows in (1, 2, half, half + 1, half + len(b), 50):
+        got = render(calls.call_chromosome_streamed(t, lambda r: _labels_for(t, labels, probs, r), opt, at,
+                                                    chunk_rows=chunk_rows))
+        assert got == whole, chunk_rows
+    # cutting at the raw region changes and flushing at every cut (what the streamed path did before the
+    # open region was held back) gives MORE records: the test discriminates
+    naive = []
+    for lo, hi in ((0, half), (half, half + len(b)), (half + len(b), len(t))):
+        naive.extend(calls.call_chromosome(t.take(slice(lo, hi)), labels[lo:hi], probs[lo:hi], opt, at))
+    assert len(naive) > len(whole[0].splitlines())

@@ -206,3 +206,19 @@ def test_real_demo_rows_and_ont_profile_match_oracle(clf, synthetic_weights):
     ref_l, ref_p, _ = alexnet.classify(encoder_c.encode_f32(rows), synthetic_weights, torch.float32, batch=100)
     assert np.array_equal(labels, ref_l.astype(np.int32))
     assert np.abs(probs - ref_p).max() < SOFTMAX_TOL
+
+
+def test_gpu_matches_the_independent_numpy_oracle(clf, synthetic_weights):
+    """The second oracle (numpy fp64 from the TF op definitions, no torch) on fresh rows: labels equal,
+    softmax within 1e-3, layerwise activations of the pooled layers within 2e-4."""
+    from oracle import alexnet_np
+    rows = np.concatenate([sites.make_sites_p2(20, seed=99), sites.make_sites_p1(12, seed=5, profile="ont")])
+    logits, inter = alexnet_np.forward(encoder_c.encode_f32(rows), synthetic_weights, return_intermediates=True)
+    labels, probs, got_logits = clf.classify_device(clf.rows_to_device(rows), want_logits=True)
+    torch.cuda.synchronize()
+    assert np.array_equal(labels.cpu().numpy(), alexnet_np.argmax_first(logits).astype(np.int32))
+    assert np.abs(probs.cpu().numpy() - alexnet_np.softmax(logits)).max() < SOFTMAX_TOL
+    assert np.abs(got_logits.cpu().numpy() - logits).max() < LOGIT_TOL
+    for name in ("norm1", "norm2", "pool5", "fc7"):
+        got, ref = clf.debug_activation(name, rows.shape[0]), inter[name]
+        assert np.abs(got - ref).max() < 2e-4 * np.abs(ref).max() + 1e-5, name
