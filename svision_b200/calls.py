@@ -29,6 +29,7 @@ import numpy as np
 TYPE_NAMES = ("DEL", "INS", "INV", "DUP", "tDUP")            # predict.py:133-142
 USE_NATIVE = True          # svx_calls_aggregate for tables parsed from BED text (tests switch it off to compare)
 MAX_GENOTYPE_ALIGNMENTS = 500                                 # genotype.py:34
+MAX_PAIRS_PER_BLOCK = 8_000_000       # (candidate, alignment) pairs genotype_many expands at once (~0.5 GB)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -122,16 +123,20 @@ class AlignmentTable:
         """One ``fetch`` over the whole contig.  Needs ``pysam`` (a dependency of the reference:
         ``setup.py:36``); raises ImportError where it is absent."""
         import pysam
+        from array import array
         bam = pysam.AlignmentFile(bam_path, "r")
-        s, e, q, u, sec, names = [], [], [], [], [], []
+        # typed arrays (8 / 1 bytes per record, amortised growth) instead of lists of Python ints
+        s, e, q, u, sec, names = array("q"), array("q"), array("q"), array("b"), array("b"), []
         for a in bam.fetch(contig=contig):
             s.append(a.reference_start)
             e.append(a.reference_end if a.reference_end is not None else a.reference_start)
             q.append(a.mapping_quality)
-            u.append(a.is_unmapped)
-            sec.append(a.is_secondary)
+            u.append(1 if a.is_unmapped else 0)
+            sec.append(1 if a.is_secondary else 0)
             names.append(a.query_name)
-        return cls(bam.get_reference_length(contig), s, e, q, u, sec, names)
+        return cls(bam.get_reference_length(contig), np.frombuffer(s, dtype=np.int64), np.frombuffer(e, dtype=np.int64),
+                   np.frombuffer(q, dtype=np.int64), np.frombuffer(u, dtype=np.int8).astype(bool),
+                   np.frombuffer(sec, dtype=np.int8).astype(bool), names)
 
     def __len__(self) -> int:
         return int(self.start.size)
@@ -177,10 +182,42 @@ class AlignmentTable:
 
 
     def genotype_many(self, candidates: Sequence, supports: Sequence[Iterable[str]], options) -> list:
-        """:meth:`genotype` for every candidate of a chromosome in one vectorised pass: the
-        (candidate, alignment) pairs of all windows are expanded side by side, filtered, capped at
-        500 usable alignments per candidate by a segmented running count, and the distinct
-        reference-supporting read names are counted per candidate."""
+        """:meth:`genotype` for every candidate of a chromosome, vectorised in blocks of bounded size: the
+        expansion below materialises one entry per (candidate, alignment in its window), which in deep
+        pile-ups (rDNA, centromeres, amplicons) is far more than the 500 alignments per record the
+        reference looks at.  Blocks hold at most MAX_PAIRS_PER_BLOCK such pairs; a candidate whose window
+        alone exceeds that goes through :meth:`genotype` (slices, no expansion)."""
+        m = len(candidates)
+        if m == 0:
+            return []
+        if len(self) == 0:
+            return self._genotype_block(candidates, supports, options)
+        start = np.array([int(c[1]) for c in candidates], dtype=np.int64)
+        end = np.array([int(c[2]) for c in candidates], dtype=np.int64)
+        lo_q, hi_q = np.maximum(0, start - 1000), np.minimum(self.contig_length, end + 1000)
+        cnt = np.where(hi_q > lo_q, np.maximum(np.searchsorted(self.start, hi_q, side="left") -
+                                               np.searchsorted(self._end_running_max, lo_q, side="right"), 0), 0)
+        if int(cnt.sum()) <= MAX_PAIRS_PER_BLOCK:
+            return self._genotype_block(candidates, supports, options)
+        out, a, load = [], 0, 0
+        for j in range(m + 1):
+            c = int(cnt[j]) if j < m else 0
+            deep = j < m and c > MAX_PAIRS_PER_BLOCK
+            if j == m or deep or load + c > MAX_PAIRS_PER_BLOCK:
+                if j > a:
+                    out.extend(self._genotype_block(candidates[a:j], supports[a:j], options))
+                a, load = j, 0
+                if deep:
+                    out.append(self.genotype(candidates[j], supports[j], options))
+                    a = j + 1
+                    continue
+            load += c
+        return out
+
+    def _genotype_block(self, candidates: Sequence, supports: Sequence[Iterable[str]], options) -> list:
+        """One vectorised pass: the (candidate, alignment) pairs of all windows are expanded side by
+        side, filtered, capped at 500 usable alignments per candidate by a segmented running count, and
+        the distinct reference-supporting read names are counted per candidate."""
         m = len(candidates)
         if m == 0:
             return []

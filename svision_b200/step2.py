@@ -220,6 +220,10 @@ def parse_arguments(argv=None):
     pred.add_argument("--homo_thresh", type=float, default=0.8)
     pred.add_argument("--hete_thresh", type=float, default=0.2)
     pred.add_argument("--device", type=int, default=0, help="CUDA device (not a reference flag)")
+    pred.add_argument("--shard", choices=("auto", "chrom", "rows"), default="auto",
+                      help="under torchrun: whole chromosomes per rank (each rank parses, classifies, aggregates "
+                           "and genotypes its own; rank 0 merges) or the rows of every chunk over the ranks; auto = "
+                           "chromosomes when there are at least as many as ranks (not a reference flag)")
     options = p.parse_args(argv)
     if options.contig:                                   # SVision:161-162
         options.min_support = 1
@@ -234,6 +238,20 @@ def chromosomes_with_segments(segments_dir: str, contigs: Sequence[Tuple[str, in
             if (want is None or name == want) and os.path.exists(os.path.join(segments_dir, name + ".segments.all.bed"))]
 
 
+def assign_chromosomes(chroms: Sequence[str], segments_dir: str, world: int) -> List[List[str]]:
+    """Whole chromosomes to ranks, longest segments file first onto the least-loaded rank (the
+    reference's pool hands one chromosome to each free worker: SVision:311-323).  Deterministic, so
+    every rank computes the same assignment; each rank's list keeps the genome's contig order."""
+    size = {c: os.path.getsize(os.path.join(segments_dir, c + ".segments.all.bed")) for c in chroms}
+    load = [0] * world
+    owner = {}
+    for c in sorted(chroms, key=lambda c: (-size[c], chroms.index(c))):
+        r = min(range(world), key=lambda k: (load[k], k))
+        owner[c] = r
+        load[r] += size[c]
+    return [[c for c in chroms if owner[c] == r] for r in range(world)]
+
+
 def main(argv=None, classifier=None, genotype_for: Optional[Callable] = None) -> int:
     options = parse_arguments(argv)
     logging.basicConfig(level=logging.INFO, format="%(asctime)s %(message)s")
@@ -244,10 +262,13 @@ def main(argv=None, classifier=None, genotype_for: Optional[Callable] = None) ->
     if not chroms:
         logging.error("no <chrom>.segments.all.bed under %s", segments_dir)
         return 1
-    # under torchrun (one process per GPU) the rows of every chunk are sharded over the ranks; every
-    # rank walks the same chromosomes so that the collectives line up, rank 0 owns the output files
+    # under torchrun (one process per GPU) either whole chromosomes go to the ranks (every rank parses,
+    # classifies, aggregates and genotypes its own chromosomes into the shared predict_results directory;
+    # rank 0 merges) or the rows of every chunk are sharded over the ranks (every rank walks the same
+    # chromosomes so that the collectives line up, rank 0 owns the output files)
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
+    by_chrom = world > 1 and (options.shard == "chrom" or (options.shard == "auto" and len(chroms) >= world))
     scratch = None
     if world > 1:
         import tempfile
@@ -256,10 +277,11 @@ def main(argv=None, classifier=None, genotype_for: Optional[Callable] = None) ->
         from . import sharded
         if not dist.is_initialized():
             os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-            dist.init_process_group("nccl" if (classifier is None and torch.cuda.is_available()) else "gloo")
+            dist.init_process_group("nccl" if (classifier is None and torch.cuda.is_available() and not by_chrom)
+                                    else "gloo")
         if classifier is None:
             options.device = int(os.environ.get("LOCAL_RANK", rank))
-        if rank != 0:                                     # same work, throw-away files, no BAM reads
+        if rank != 0 and not by_chrom:                    # same work, throw-away files, no BAM reads
             scratch = tempfile.mkdtemp(prefix=f"svx_step2_rank{rank}_")
             predict_dir = os.path.join(scratch, "predict_results")
             options.out_path = scratch
@@ -267,10 +289,22 @@ def main(argv=None, classifier=None, genotype_for: Optional[Callable] = None) ->
                 genotype_for = lambda chrom: (lambda *a: ("./.", 0, 0))    # noqa: E731
     if classifier is None:
         classifier = _predict.get_classifier(options.model_path, device=options.device)
-    if world > 1:
-        classifier = sharded.ShardedClassifier(classifier)
     try:
-        merged = run_step2(chroms, segments_dir, predict_dir, options, classifier, genotype_for, contigs)
+        if by_chrom:
+            mine = assign_chromosomes(chroms, segments_dir, world)[rank]
+            done = predict_chromosomes(mine, segments_dir, predict_dir, options, classifier, genotype_for)
+            everyone = [None] * world
+            dist.all_gather_object(everyone, sorted(done))               # also the barrier: all files are written
+            merged = os.path.join(options.out_path, f"{options.sample}.svision.s{options.min_support}.vcf")
+            if rank == 0:
+                have = {c for part in everyone for c in part}
+                hi, lo = score_range(predict_dir)
+                merge_chromosomes(predict_dir, merged, hi, lo, [c for c in chroms if c in have], options, contigs)
+            dist.barrier()
+        else:
+            if world > 1:
+                classifier = sharded.ShardedClassifier(classifier)
+            merged = run_step2(chroms, segments_dir, predict_dir, options, classifier, genotype_for, contigs)
     except ValueError as e:                               # 'Empty output in the score file' (SVision:374-376)
         logging.error("%s", e)
         return 1

@@ -377,3 +377,23 @@ def test_streamed_seams_do_not_split_a_region_whose_interruption_is_dropped(gold
     for lo, hi in ((0, half), (half, half + len(b)), (half + len(b), len(t))):
         naive.extend(calls.call_chromosome(t.take(slice(lo, hi)), labels[lo:hi], probs[lo:hi], opt, at))
     assert len(naive) > len(whole[0].splitlines())
+
+
+def test_genotype_many_in_bounded_blocks_equals_one_pass(golden, monkeypatch):
+    """Deep pile-ups: the vectorised genotyper works in blocks of bounded size and sends windows deeper
+    than a block through the per-candidate route; the answers do not change."""
+    g, table, aln = golden
+    at = make_table(aln)
+    opt = G.options(1, True)
+    records = calls.call_chromosome(table, g["labels"], g["probs"], opt, lambda *a: ("./.", 0, 0))
+    cands, sups = [], []
+    for _, line in records[:400]:
+        f = line.split("\t")
+        info = dict(kv.split("=", 1) for kv in f[7].split(";") if "=" in kv)
+        cands.append((f[0], int(f[1]), int(info["END"]), info["SVTYPE"].split("+")))
+        sups.append(info.get("READS", "").split(","))
+    whole = at.genotype_many(cands, sups, opt)
+    assert whole == [at.genotype(c, s, opt) for c, s in zip(cands, sups)]
+    for cap in (1, 50, 3000):                                # 1: every window is "deep" -> per-candidate route
+        monkeypatch.setattr(calls, "MAX_PAIRS_PER_BLOCK", cap)
+        assert at.genotype_many(cands, sups, opt) == whole

@@ -118,6 +118,51 @@ def test_config4_stream_to_vcf_matches_oracle_pipeline(clf, synthetic_weights, t
             assert f1[:5] == f2[:5] and f1[6:] == f2[6:]          # POS/ID/ALT, INFO, GT:DR:DV identical
 
 
+CONFIG4_GOLDEN = os.path.join(os.path.dirname(__file__), "golden", "config4_oracle_calls.npz")
+NEAR_TIE = 2e-3             # top-2 logit margin below which a label may legitimately differ (GPU logit error <= 4e-4)
+
+
+@pytest.mark.skipif(not os.path.exists(CONFIG4_GOLDEN), reason="oracle calls of the 500k stream not generated")
+def test_config4_whole_500k_stream_against_committed_oracle_calls(synthetic_weights):
+    """BASELINE configs[3]: the WHOLE ~500 k-row HiFi stream (seed 20261019) on the GPU against the CPU
+    oracle's calls for every row (tests/golden/config4_oracle_calls.npz, oracle/make_config4_golden.py):
+    labels equal except at near-ties of the oracle's own top-2 logits (counted, < 0.01 % of rows),
+    scores within 1e-3, and the VCF text of the two pipelines: same records, QUAL within +-2."""
+    g = np.load(CONFIG4_GOLDEN)
+    n, seed = (int(v) for v in g["meta"])
+    assert seed == sites.SEED_CONFIG4
+    table = sites.make_region_table(n, seed=seed, profile="hifi")
+    with C.Classifier(synthetic_weights, device=0, max_batch=8192) as big:
+        labels, probs = big.classify(table.rows)
+    ref_l, ref_s, margin = g["labels"].astype(np.int32), g["score"], g["margin"]
+    diff = np.flatnonzero(labels != ref_l)
+    assert (margin[diff] < NEAR_TIE).all(), f"label differs away from a near-tie at rows {diff[margin[diff] >= NEAR_TIE][:10]}"
+    assert diff.size <= n // 10_000, f"{diff.size} label differences"
+    same = labels == ref_l
+    win = probs[np.arange(n), labels]
+    assert np.abs(win[same] - ref_s[same]).max() < SOFTMAX_TOL
+    # VCF parity: at the (few) near-tie rows both pipelines take the oracle's call, everywhere else
+    # each pipeline uses its own labels and scores
+    aln = sites.make_alignments(table, seed=2)
+    at = calls.AlignmentTable(aln["contig_length"], aln["reference_start"], aln["reference_end"],
+                              aln["mapping_quality"], aln["is_unmapped"], aln["is_secondary"], aln["query_name"])
+    ref_p = np.zeros((n, 5), np.float32)
+    ref_p[np.arange(n), ref_l] = ref_s
+    gpu_l, gpu_p = labels.copy(), probs.copy()
+    gpu_l[diff], gpu_p[diff] = ref_l[diff], ref_p[diff]
+    opt = _options(3)
+    got = calls.call_chromosome(table, gpu_l, gpu_p, opt, at)
+    ref = calls.call_chromosome(table, ref_l, ref_p, opt, at)
+    assert len(got) == len(ref) > 10_000
+    worst = 0.0
+    for (q1, line1), (q2, line2) in zip(got, ref):
+        f1, f2 = line1.split("\t"), line2.split("\t")
+        worst = max(worst, abs(float(q1) - float(q2)))
+        assert f1[:5] == f2[:5] and f1[6:] == f2[6:]              # POS/ID/ALT, INFO, GT:DR:DV identical
+    assert worst <= 2
+    print(f"config4: {n} rows, {diff.size} near-tie label differences, {len(got)} records, max |dQUAL| {worst:.3f}")
+
+
 def test_config1_demo_bed_through_step2_on_the_gpu(clf, synthetic_weights, tmp_path):
     """BASELINE config 1's rows (the reference's collection stage on its demo BAM, committed as
     tests/golden/demo_chr9.segments.bed) through the whole Step 2 on the GPU classifier: per-chromosome

@@ -184,9 +184,12 @@ def _step2_worker(rank, world, port, argv, q):
     dist.destroy_process_group()
 
 
-def test_command_line_under_torchrun_shards_rows_over_ranks_gloo_world2(tmp_path):
-    """Two ranks (gloo, CPU): every chunk's rows are sharded over the ranks, rank 0 writes the files;
-    the merged VCF equals the single-process run."""
+@pytest.mark.parametrize("shard", ["rows", "chrom"])
+def test_command_line_under_torchrun_gloo_world2(tmp_path, shard):
+    """Two ranks (gloo, CPU).  rows: every chunk's rows are sharded over the ranks, rank 0 writes the
+    files.  chrom: every rank runs whole chromosomes of its own (parse, classify, aggregate, genotype)
+    into the shared directory and rank 0 merges.  Either way the merged VCF equals the single-process
+    run."""
     import torch.multiprocessing as mp
     seg_dir, _, _, _ = _prepare(tmp_path)
     outs = {}
@@ -197,7 +200,7 @@ def test_command_line_under_torchrun_shards_rows_over_ranks_gloo_world2(tmp_path
             (out / "segments" / f).write_bytes(open(os.path.join(seg_dir, f), "rb").read())
         outs[name] = out
     argv = lambda out: ["-o", str(out), "-b", "x.bam", "-m", "x.ckpt", "-g", str(tmp_path / "genome.fa"),   # noqa: E731
-                        "-n", "S", "-s", "2", "--qname"]
+                        "-n", "S", "-s", "2", "--qname", "--shard", shard, "--debug"]
     assert step2.main(argv(outs["single"]), classifier=HashClassifier(),
                       genotype_for=lambda chrom: (lambda *a: ("0/1", 3, 4))) == 0
     ctx = mp.get_context("spawn")
@@ -213,3 +216,8 @@ def test_command_line_under_torchrun_shards_rows_over_ranks_gloo_world2(tmp_path
     a = (outs["single"] / "S.svision.s2.vcf").read_text()
     b = (outs["sharded"] / "S.svision.s2.vcf").read_text()
     assert a == b and a.count("\n") > 100
+    if shard == "chrom":                                 # the ranks wrote disjoint chromosomes into ONE directory
+        files = sorted(f for f in os.listdir(outs["sharded"] / "predict_results") if f.endswith(".vcf"))
+        assert files == sorted(f for f in os.listdir(outs["single"] / "predict_results") if f.endswith(".vcf"))
+        parts = step2.assign_chromosomes(["chr1", "chr2", "chrX"], str(outs["sharded"] / "segments"), 2)
+        assert sorted(c for p in parts for c in p) == ["chr1", "chr2", "chrX"] and all(parts)

@@ -7,9 +7,11 @@
 Rank 0 prepares <out>/segments/<chrom>.segments.all.bed (synthetic region-grouped streams), a genome
 .fai and a TF-format checkpoint of the synthetic weights (written with svision_b200.tf_bundle, read back
 through the -m loader, so the TF-free reader is on the path), then every rank runs
-``svision_b200.step2.main`` with the reference's flags.  Genotypes come from synthetic alignment tables
-(reading a real BAM needs pysam, as in the reference).  Prints one JSON line on rank 0: rows/s of the
-whole step and the digest of the merged VCF (equal for every world size)."""
+``svision_b200.step2.main`` with the reference's flags (--shard auto: whole chromosomes per rank when
+there are at least as many chromosomes as ranks, else the rows of every chunk over the ranks).
+Genotypes come from synthetic alignment tables built by the rank that owns the chromosome (reading a
+real BAM needs pysam, as in the reference).  Prints one JSON line on rank 0: rows/s of the whole step
+and the digest of the merged VCF (equal for every world size and sharding mode)."""
 import argparse
 import hashlib
 import json
@@ -29,6 +31,7 @@ def main():
     ap.add_argument("--rows", type=int, default=200_000, help="rows per chromosome")
     ap.add_argument("--chroms", type=int, default=3)
     ap.add_argument("--out", default=None)
+    ap.add_argument("--shard", default="auto", choices=["auto", "chrom", "rows"])
     a = ap.parse_args()
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
     out = a.out or os.path.join(tempfile.gettempdir(), "svx_step2_demo")
@@ -39,10 +42,13 @@ def main():
         torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", rank)))
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl")
+    def table_of(k):
+        return sites.make_region_table(a.rows, seed=sites.SEED_CONFIG4 + 10 * k, contig=names[k])
+
     tables = {}
-    for k, chrom in enumerate(names):                    # every rank builds the same streams (seeded)
-        tables[chrom] = sites.make_region_table(a.rows, seed=sites.SEED_CONFIG4 + 10 * k, contig=chrom)
     if rank == 0:
+        for k, chrom in enumerate(names):
+            tables[chrom] = table_of(k)
         os.makedirs(os.path.join(out, "segments"), exist_ok=True)
         for chrom, t in tables.items():
             with open(os.path.join(out, "segments", chrom + ".segments.all.bed"), "w") as f:
@@ -52,27 +58,36 @@ def main():
         tf_bundle.write_bundle(os.path.join(out, "model.ckpt"), weights.synthetic_weights())
     if world > 1:
         dist.barrier()
+    # alignment tables (standing for the chromosome's BAM records) of the chromosomes this rank will
+    # genotype: its own under chromosome sharding, all of them on rank 0 otherwise; built before the clock
+    by_chrom = world > 1 and (a.shard == "chrom" or (a.shard == "auto" and a.chroms >= world))
+    mine = step2.assign_chromosomes(names, os.path.join(out, "segments"), world)[rank] if by_chrom else \
+        (names if rank == 0 else [])
     aligns = {}
-    if rank == 0:
-        for k, chrom in enumerate(names):
-            al = sites.make_alignments(tables[chrom], seed=7 + k)
-            aligns[chrom] = calls.AlignmentTable(al["contig_length"], al["reference_start"], al["reference_end"],
-                                                 al["mapping_quality"], al["is_unmapped"], al["is_secondary"],
-                                                 al["query_name"])
+    for chrom in mine:
+        k = names.index(chrom)
+        al = sites.make_alignments(tables[chrom] if chrom in tables else table_of(k), seed=7 + k)
+        aligns[chrom] = calls.AlignmentTable(al["contig_length"], al["reference_start"], al["reference_end"],
+                                             al["mapping_quality"], al["is_unmapped"], al["is_secondary"],
+                                             al["query_name"])
+
     argv = ["-o", out, "-b", "synthetic.bam", "-m", os.path.join(out, "model.ckpt"), "-g", os.path.join(out, "genome.fa"),
-            "-n", "demo", "-s", "3", "--debug"]
+            "-n", "demo", "-s", "3", "--debug", "--shard", a.shard]
     from svision_b200 import predict
     t = time.perf_counter()                                # -m loader (TF bundle, no TF) + weight repack + workspaces
     clf = predict.get_classifier(os.path.join(out, "model.ckpt"), device=int(os.environ.get("LOCAL_RANK", rank)))
-    clf.classify(tables[names[0]].rows[:4096])             # first-launch warm-up
+    clf.classify(sites.make_sites_p1(4096))               # first-launch warm-up
     t_model = time.perf_counter() - t
+    if world > 1:
+        dist.barrier()
     t = time.perf_counter()
-    rc = step2.main(argv, classifier=clf, genotype_for=aligns.get if rank == 0 else None)
+    rc = step2.main(argv, classifier=clf, genotype_for=aligns.get if (rank == 0 or by_chrom) else None)
     dt = time.perf_counter() - t
     if rank == 0:
         merged = os.path.join(out, "demo.svision.s3.vcf")
         text = open(merged, "rb").read()
-        print(json.dumps({"world": world, "rc": rc, "chromosomes": a.chroms, "rows": a.rows * a.chroms,
+        print(json.dumps({"world": world, "rc": rc, "shard": "chrom" if by_chrom else ("rows" if world > 1 else "none"),
+                          "chromosomes": a.chroms, "rows": a.rows * a.chroms,
                           "model_load_s": round(t_model, 3), "step2_s": round(dt, 3), "rows_per_s": round(a.rows * a.chroms / dt),
                           "records": sum(1 for l in text.split(b"\n") if l and not l.startswith(b"#")),
                           "merged_sha256": hashlib.sha256(text).hexdigest()}), flush=True)
