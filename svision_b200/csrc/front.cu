@@ -13,25 +13,25 @@
 // -- the same dense convolution with its terms regrouped; only fp32 rounding order differs.  An
 // image has <= ~1100 lit channel-pixels of 154 587, so > 80 % of the pooled 27x27 positions see
 // pure background (one precomputed 96-vector) and the rest need a few dozen FMAs per channel
-// instead of 3 267 MACs.  The dense tcgen05 conv1 (conv_tc.cu) remains the path for arbitrary
+// instead of 3 267 MACs.  The dense tcgen05 conv1 (layer_tc.cu) remains the path for arbitrary
 // images (svx_forward) and the parity tests cross-check the two.
 //
 // One CTA per site: bitmap in shared memory (encoder_bitmap.cuh, bit-exact with the reference
 // rasteriser); the lit pixels mark the conv1 positions whose 11x11 window they fall in (~350 of
 // 3 025) and those mark the pooled positions that see them (~140 of 729).  Background pooled
-// positions are streamed out with 16-byte stores.  Phase A: one warp per dirty conv1 position
-// walks the lit pixels of its window once, lane = 3 consecutive output channels (weight reads are
-// coalesced over n), result to a per-CTA scratch that stays in L2.  Phase B: one warp per dirty
-// pooled position takes the max over its 3x3 conv positions (scratch value, or the background
-// value), ReLU, LRN by shuffle, fp16 hi/lo split.  (The first version recomputed every conv
-// position for each of the up to four pooled windows containing it.)
+// positions are streamed out with 16-byte stores.  Phase A: a quarter-warp per dirty conv1 position
+// walks the lit pixels of its window once, lane = 12 consecutive output channels (16-byte weight
+// loads), result to a per-CTA scratch that stays in L2.  Phase B: one warp per dirty pooled position
+// (lanes 0..23 = 4 channels each) takes the max over its 3x3 conv positions (scratch value, or the
+// background value), ReLU, LRN by shuffle, fp16 hi/lo split.  ncu (round 2) had phase B at ~45 % of
+// the kernel's instructions with 3-channel lanes: every lane repeated the nine slot lookups and
+// issued 27 four-byte loads that used 14 of every 32 bytes fetched; now lanes 0..8 look the slots up
+// and broadcast them, and a position's nine conv vectors are nine 16-byte loads per lane.
 #include "common.cuh"
 #include "encoder_bitmap.cuh"
 #include "kernels.h"
 
 #include <math_constants.h>
-
-#include <cstdlib>
 
 namespace svx {
 
@@ -43,28 +43,22 @@ constexpr int POOLED = 27;
 constexpr int NPOS = POOLED * POOLED;        // 729
 constexpr int G2W = 29, G2POS = G2W * G2W;   // conv2 operand grid (27 + 2 shared pad)
 
-// bits [c, c+19) of bitmap row r (c + 18 <= 226, so both words lie inside the row)
-__device__ __forceinline__ uint32_t window19(const uint32_t* plane, int r, int c) {
-    const uint32_t* rowp = plane + r * BMW;
-    const int wi = c >> 5;
-    return __funnelshift_r(rowp[wi], rowp[wi + 1], c & 31) & 0x7FFFFu;
-}
-
-// LRN over channels with lane = 3 consecutive channels (radius 2, alpha 2e-5, beta .75, bias 1)
-__device__ __forceinline__ void lrn3(const float (&m)[3], float (&out)[3], int lane) {
-    float sq[7];
+// LRN over channels with lane = 4 consecutive channels, lanes 0..23 (radius 2, alpha 2e-5, beta .75,
+// bias 1); lanes 24..31 must hold zeros (they are the zero padding above channel 95)
+__device__ __forceinline__ void lrn4(const float (&m)[4], float (&out)[4], int lane) {
+    float sq[8];
 #pragma unroll
-    for (int j = 0; j < 3; ++j) sq[j + 2] = m[j] * m[j];
-    const float l0 = __shfl_up_sync(0xffffffffu, sq[3], 1);
-    const float l1 = __shfl_up_sync(0xffffffffu, sq[4], 1);
-    const float r0 = __shfl_down_sync(0xffffffffu, sq[2], 1);
+    for (int j = 0; j < 4; ++j) sq[j + 2] = m[j] * m[j];
+    const float l0 = __shfl_up_sync(0xffffffffu, sq[4], 1);       // lane-1's channels 2, 3
+    const float l1 = __shfl_up_sync(0xffffffffu, sq[5], 1);
+    const float r0 = __shfl_down_sync(0xffffffffu, sq[2], 1);     // lane+1's channels 0, 1
     const float r1 = __shfl_down_sync(0xffffffffu, sq[3], 1);
     sq[0] = lane > 0 ? l0 : 0.f;
     sq[1] = lane > 0 ? l1 : 0.f;
-    sq[5] = lane < 31 ? r0 : 0.f;
-    sq[6] = lane < 31 ? r1 : 0.f;
+    sq[6] = lane < 31 ? r0 : 0.f;
+    sq[7] = lane < 31 ? r1 : 0.f;
 #pragma unroll
-    for (int j = 0; j < 3; ++j) {
+    for (int j = 0; j < 4; ++j) {
         const float s5 = sq[j] + sq[j + 1] + sq[j + 2] + sq[j + 3] + sq[j + 4];
         out[j] = m[j] * pow_m075(1.0f + 2e-5f * s5);
     }
@@ -126,23 +120,25 @@ front_kernel(const int32_t* __restrict__ rows, long long n, const FrontParams P)
     __shared__ int dirty_count, conv_count;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int c3 = 3 * lane;                                // this lane's first channel
+    // phase B and the background vector: lanes 0..23 own 4 consecutive channels (16-byte loads)
+    const int c4 = 4 * lane;
+    const bool chan = lane < 24;
     float* __restrict__ scratch = P.scratch + (size_t)blockIdx.x * SCRATCH_SLOTS * 96;
 
-    float base3[3];
-#pragma unroll
-    for (int j = 0; j < 3; ++j) base3[j] = P.base[c3 + j];
+    float4 base4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (chan) base4 = __ldg(reinterpret_cast<const float4*>(P.base + c4));
     // background value of every pooled position: LRN(ReLU(base)) (max-pool of a constant)
     if (warp == 0) {
-        float m[3], o[3];
+        const float m[4] = {fmaxf(base4.x, 0.f), fmaxf(base4.y, 0.f), fmaxf(base4.z, 0.f), fmaxf(base4.w, 0.f)};
+        float o[4];
+        lrn4(m, o, lane);
+        if (chan) {
 #pragma unroll
-        for (int j = 0; j < 3; ++j) m[j] = fmaxf(base3[j], 0.f);
-        lrn3(m, o, lane);
-#pragma unroll
-        for (int j = 0; j < 3; ++j) {
-            const __half h = __float2half_rn(o[j]);
-            bg[0][c3 + j] = __half_as_ushort(h);
-            bg[1][c3 + j] = __half_as_ushort(__float2half_rn(o[j] - __half2float(h)));
+            for (int j = 0; j < 4; ++j) {
+                const __half h = __float2half_rn(o[j]);
+                bg[0][c4 + j] = __half_as_ushort(h);
+                bg[1][c4 + j] = __half_as_ushort(__float2half_rn(o[j] - __half2float(h)));
+            }
         }
     }
 
@@ -201,7 +197,7 @@ front_kernel(const int32_t* __restrict__ rows, long long n, const FrontParams P)
             }
             if (any) {
                 atomicOr(&dirty_mask[p >> 5], 1u << (p & 31));
-                dirty_list[atomicAdd(&dirty_count, 1)] = (unsigned short)p;
+                dirty_list[atomicAdd(&dirty_count, 1)] = (unsigned short)((py << 5) | px);
             }
         }
         __syncthreads();
@@ -270,67 +266,64 @@ front_kernel(const int32_t* __restrict__ rows, long long n, const FrontParams P)
         }
         __syncthreads();                                    // scratch visible to the whole CTA
 
-        // ---- phase B: flagged pooled positions: max over the 3x3 conv positions, LRN, store
+        // ---- phase B: flagged pooled positions: max over the 3x3 conv positions, LRN, store.  One warp
+        //      per position.  The nine scratch slots are looked up by lanes 0..8 and broadcast; if none
+        //      overflowed the scratch (never, with two segments) the nine conv vectors are fetched with
+        //      independent predicated 16-byte loads: one L2 round trip per pooled position
         const int nd = dirty_count;
         for (int i = warp; i < nd; i += FRONT_THREADS / 32) {
-            const int p = dirty_list[i];
-            const int py = p / POOLED, px = p - py * POOLED;
-            float m[3] = {0.f, 0.f, 0.f}, o[3];              // ReLU folded into the max with 0
-            // all nine slots first; if none overflowed the scratch (never, with two segments), nine
-            // independent predicated loads: one L2 round trip per position instead of one per dirty
-            // conv position
-            unsigned short sl[9];
-            bool overflow = false;
-#pragma unroll
-            for (int k = 0; k < 9; ++k) {
-                sl[k] = cslot[(2 * py + k / 3) * CONV_W + 2 * px + (k % 3)];
-                overflow |= sl[k] != CLEAN && sl[k] >= SCRATCH_SLOTS;
-            }
-            if ((P.flags & 1) && !overflow) {
-                float v[9][3];
+            const int code = dirty_list[i];
+            const int py = code >> 5, px = code & 31;
+            int my_slot = CLEAN;
+            if (lane < 9) my_slot = cslot[(2 * py + lane / 3) * CONV_W + 2 * px + (lane % 3)];
+            const bool overflow = __any_sync(0xffffffffu, my_slot != CLEAN && my_slot >= SCRATCH_SLOTS);
+            float m[4] = {0.f, 0.f, 0.f, 0.f}, o[4];         // ReLU folded into the max with 0
+            if (!overflow) {
+                float4 v[9];
 #pragma unroll
                 for (int k = 0; k < 9; ++k) {
-                    const bool ld = sl[k] != CLEAN;
-                    const float* q = scratch + (int)(ld ? sl[k] : 0) * 96 + c3;
-#pragma unroll
-                    for (int j = 0; j < 3; ++j)
-                        v[k][j] = ld ? ((P.flags & 2) ? q[j] : __ldcg(q + j)) : base3[j];   // clean: background
+                    const int sl = __shfl_sync(0xffffffffu, my_slot, k);
+                    v[k] = base4;                            // clean conv positions hold the background value
+                    if (sl != CLEAN && chan) v[k] = *reinterpret_cast<const float4*>(scratch + sl * 96 + c4);
                 }
 #pragma unroll
-                for (int k = 0; k < 9; ++k)
-#pragma unroll
-                    for (int j = 0; j < 3; ++j) m[j] = fmaxf(m[j], v[k][j]);
+                for (int k = 0; k < 9; ++k) {
+                    m[0] = fmaxf(m[0], v[k].x); m[1] = fmaxf(m[1], v[k].y);
+                    m[2] = fmaxf(m[2], v[k].z); m[3] = fmaxf(m[3], v[k].w);
+                }
             } else {
-                bool all_dirty = true;
-#pragma unroll
+#pragma unroll 1
                 for (int k = 0; k < 9; ++k) {
-                    if (sl[k] == CLEAN) { all_dirty = false; continue; }
-                    if (sl[k] < SCRATCH_SLOTS) {
-                        const float* v = scratch + (int)sl[k] * 96 + c3;
-                        if (P.flags & 2) {
-                            m[0] = fmaxf(m[0], v[0]); m[1] = fmaxf(m[1], v[1]); m[2] = fmaxf(m[2], v[2]);
-                        } else {
-                            m[0] = fmaxf(m[0], __ldcg(v)); m[1] = fmaxf(m[1], __ldcg(v + 1)); m[2] = fmaxf(m[2], __ldcg(v + 2));
+                    const int sl = __shfl_sync(0xffffffffu, my_slot, k);
+                    float4 v = base4;
+                    if (chan) {
+                        if (sl != CLEAN && sl < SCRATCH_SLOTS) {
+                            v = *reinterpret_cast<const float4*>(scratch + sl * 96 + c4);
+                        } else if (sl != CLEAN) {            // beyond the scratch capacity: recompute here
+                            float r[4];
+                            conv1_at<4>(bm, P, 2 * py + k / 3, 2 * px + (k % 3), c4, r);
+                            v = make_float4(r[0], r[1], r[2], r[3]);
                         }
-                    } else {                             // beyond the scratch capacity: recompute here
-                        float v[3];
-                        conv1_at<3>(bm, P, 2 * py + k / 3, 2 * px + (k % 3), c3, v);
-                        m[0] = fmaxf(m[0], v[0]); m[1] = fmaxf(m[1], v[1]); m[2] = fmaxf(m[2], v[2]);
                     }
-                }
-                if (!all_dirty) {                            // clean conv positions hold the background value
-#pragma unroll
-                    for (int j = 0; j < 3; ++j) m[j] = fmaxf(m[j], base3[j]);
+                    m[0] = fmaxf(m[0], v.x); m[1] = fmaxf(m[1], v.y);
+                    m[2] = fmaxf(m[2], v.z); m[3] = fmaxf(m[3], v.w);
                 }
             }
-            lrn3(m, o, lane);
-            const long long off =
-                (long long)(c3 / 48) * P.group_elems + (img_row0 + py * G2W + px) * P.ld + (c3 % 48);
+            lrn4(m, o, lane);                                // lanes 24..31 carry zeros
+            if (chan) {
+                const long long off =
+                    (long long)(c4 / 48) * P.group_elems + (img_row0 + py * G2W + px) * P.ld + (c4 % 48);
+                uint32_t ph[2], pl[2];
 #pragma unroll
-            for (int j = 0; j < 3; ++j) {
-                const __half h = __float2half_rn(o[j]);
-                P.x2_hi[off + j] = h;
-                P.x2_lo[off + j] = __float2half_rn(o[j] - __half2float(h));
+                for (int j = 0; j < 2; ++j) {
+                    const __half h0 = __float2half_rn(o[2 * j]), h1 = __float2half_rn(o[2 * j + 1]);
+                    const __half e0 = __float2half_rn(o[2 * j] - __half2float(h0));
+                    const __half e1 = __float2half_rn(o[2 * j + 1] - __half2float(h1));
+                    ph[j] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
+                    pl[j] = (uint32_t)__half_as_ushort(e0) | ((uint32_t)__half_as_ushort(e1) << 16);
+                }
+                *reinterpret_cast<uint2*>(P.x2_hi + off) = make_uint2(ph[0], ph[1]);
+                *reinterpret_cast<uint2*>(P.x2_lo + off) = make_uint2(pl[0], pl[1]);
             }
         }
         if (tid < 12) rowbuf[cur ^ 1][tid] = pre;
@@ -352,9 +345,7 @@ int launch_front(const int32_t* rows_dev, long long n, const FrontParams& P, int
         // 4 CTAs x 38 KB of shared memory fit the 164 KB configuration, which leaves ~90 KB of L1 for
         // the conv1 weight vectors phase A walks (the channel-0 vectors alone are 46 KB); with the
         // maximum carve-out L1 was ~25 KB and half of those loads went to L2
-        int carve = 72;
-        if (const char* e = std::getenv("SVX_FRONT_CARVEOUT")) carve = std::atoi(e);
-        cudaFuncSetAttribute(front_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
+        cudaFuncSetAttribute(front_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 72);
         int nb = 0;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, front_kernel, bitmap::FRONT_THREADS, 0) !=
                 cudaSuccess || nb < 1)

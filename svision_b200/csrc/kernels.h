@@ -23,7 +23,6 @@ struct FrontParams {
     int scratch_blocks;        // upper bound for the grid
     int ld;                    // elements per position row (128 padded layout, 48 packed layout)
     long long group_elems;     // element offset of channel group 1 (64 padded, plane size packed)
-    int flags;                 // phase B: bit0 batched slot loads, bit1 L1-cached scratch loads
 };
 int launch_front(const int32_t* rows_dev, long long n, const FrontParams& P, int num_sms,
                  cudaStream_t stream);

@@ -473,7 +473,7 @@ long long balanced_batch(long long n, long long max_batch) {
 // rows -> conv2 operand: the fused sparse front end (encode + conv1 + ReLU + pool1 + LRN1)
 int encode_front(svx_handle* h, const int32_t* rows_dev, long long m, cudaStream_t st) {
     FrontParams fp{h->front_w255, h->front_base, h->x2_hi, h->x2_lo, h->front_scratch, h->front_blocks,
-                   h->x2_ld, h->x2_group_elems, 3};
+                   h->x2_ld, h->x2_group_elems};
     mark(h, 0, st);
     return launch_front(rows_dev, m, fp, h->num_sms, st);
 }
