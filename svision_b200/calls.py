@@ -24,6 +24,9 @@ from __future__ import annotations
 from collections import Counter
 from typing import Callable, Iterable, List, Optional, Sequence, Tuple
 
+import logging
+import time
+
 import numpy as np
 
 TYPE_NAMES = ("DEL", "INS", "INV", "DUP", "tDUP")            # predict.py:133-142
@@ -509,7 +512,9 @@ def call_chromosome_streamed(table, classify: Callable, options, genotype, chunk
     with ThreadPoolExecutor(max_workers=1) as pool:
         pending = pool.submit(classify, np.ascontiguousarray(table.rows[spans[0][0]:spans[0][1]]))
         for k, (a, b) in enumerate(spans):
+            t_wait = time.perf_counter()
             labels, probs = pending.result()
+            t_host = time.perf_counter()
             if k + 1 < len(spans):
                 na, nb = spans[k + 1]
                 pending = pool.submit(classify, np.ascontiguousarray(table.rows[na:nb]))
@@ -522,6 +527,8 @@ def call_chromosome_streamed(table, classify: Callable, options, genotype, chunk
                                                labels[:cut], probs[:cut], options, genotype, aggregate))
             held_l, held_p = labels[cut:], probs[cut:]
             start += cut
+            logging.debug("chunk %d: rows [%d, %d): waited %.3f s for the classifier, host %.3f s", k, a, b,
+                          t_host - t_wait, time.perf_counter() - t_host)
     return records
 
 

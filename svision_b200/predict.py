@@ -97,7 +97,10 @@ def run_predict(segments_out_file: str, out_path_prefix: str, options, aggregate
     then a :class:`calls.AlignmentTable`, a callable ``(candidate, read_names, options) -> (GT, DR, DV)``,
     or None to load ``options.bam_path`` once for ``chrom`` (needs pysam, as the reference does).
     Returns the number of regions flushed (injected mode) or of records written (default mode)."""
+    import time
+    t0 = time.perf_counter()
     table = _bed.read_segments_bed(segments_out_file)
+    t_parse = time.perf_counter() - t0
     clf = classifier if classifier is not None else get_classifier(options.model_path)
     if chrom:
         logging.info("Predicting " + chrom)                           # predict.py:204
@@ -107,9 +110,14 @@ def run_predict(segments_out_file: str, out_path_prefix: str, options, aggregate
             contig = chrom if chrom else (str(table.region[0]).split("+")[0] if len(table) else None)
             genotype = calls.AlignmentTable.from_bam(options.bam_path, contig) if contig else (lambda *a: ("./.", 0, 0))
         # classification of the next chunk of regions overlaps the record assembly of this one
+        t0 = time.perf_counter()
         records = calls.call_chromosome_streamed(table, clf.classify, options, genotype,
                                                  chunk_rows=getattr(options, "chunk_rows", 65536))
+        t_calls = time.perf_counter() - t0
         calls.write_chromosome(out_path_prefix, records)
+        logging.info("%s: %d rows: parse %.3f s, classify + calls %.3f s, write %.3f s -> %d records",
+                     chrom or segments_out_file, len(table), t_parse, t_calls, time.perf_counter() - t0 - t_calls,
+                     len(records))
         return len(records)
     if aggregate is None or write is None:
         raise ValueError("inject both of the reference's aggregate and write functions, or neither")

@@ -254,7 +254,8 @@ def assign_chromosomes(chroms: Sequence[str], segments_dir: str, world: int) -> 
 
 def main(argv=None, classifier=None, genotype_for: Optional[Callable] = None) -> int:
     options = parse_arguments(argv)
-    logging.basicConfig(level=logging.INFO, format="%(asctime)s %(message)s")
+    logging.basicConfig(level=logging.DEBUG if os.environ.get("SVX_STEP2_DEBUG") else logging.INFO,
+                        format="%(asctime)s %(message)s")
     segments_dir = os.path.join(options.out_path, "segments")
     predict_dir = os.path.join(options.out_path, "predict_results")
     contigs = contigs_from_fai(options.genome)
@@ -291,16 +292,23 @@ def main(argv=None, classifier=None, genotype_for: Optional[Callable] = None) ->
         classifier = _predict.get_classifier(options.model_path, device=options.device)
     try:
         if by_chrom:
+            import time
+            t0 = time.perf_counter()
             mine = assign_chromosomes(chroms, segments_dir, world)[rank]
             done = predict_chromosomes(mine, segments_dir, predict_dir, options, classifier, genotype_for)
+            t1 = time.perf_counter()
             everyone = [None] * world
             dist.all_gather_object(everyone, sorted(done))               # also the barrier: all files are written
+            t2 = time.perf_counter()
             merged = os.path.join(options.out_path, f"{options.sample}.svision.s{options.min_support}.vcf")
             if rank == 0:
                 have = {c for part in everyone for c in part}
                 hi, lo = score_range(predict_dir)
                 merge_chromosomes(predict_dir, merged, hi, lo, [c for c in chroms if c in have], options, contigs)
+            t3 = time.perf_counter()
             dist.barrier()
+            logging.info("rank %d: own chromosomes %s in %.3f s, waited %.3f s for the others, merge %.3f s",
+                         rank, ",".join(mine), t1 - t0, t2 - t1, t3 - t2)
         else:
             if world > 1:
                 classifier = sharded.ShardedClassifier(classifier)

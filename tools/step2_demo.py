@@ -45,14 +45,16 @@ def main():
     def table_of(k):
         return sites.make_region_table(a.rows, seed=sites.SEED_CONFIG4 + 10 * k, contig=names[k])
 
+    # every rank prepares the segment files of chromosomes k = rank (mod world): Step 1's output
     tables = {}
+    os.makedirs(os.path.join(out, "segments"), exist_ok=True)
+    for k, chrom in enumerate(names):
+        if k % world != rank:
+            continue
+        tables[chrom] = table_of(k)
+        with open(os.path.join(out, "segments", chrom + ".segments.all.bed"), "w") as f:
+            f.write("\n".join(sites.table_to_bed_lines(tables[chrom])) + "\n")
     if rank == 0:
-        for k, chrom in enumerate(names):
-            tables[chrom] = table_of(k)
-        os.makedirs(os.path.join(out, "segments"), exist_ok=True)
-        for chrom, t in tables.items():
-            with open(os.path.join(out, "segments", chrom + ".segments.all.bed"), "w") as f:
-                f.write("\n".join(sites.table_to_bed_lines(t)) + "\n")
         with open(os.path.join(out, "genome.fa.fai"), "w") as f:
             f.writelines(f"{c}\t250000000\t0\t70\t71\n" for c in names)
         tf_bundle.write_bundle(os.path.join(out, "model.ckpt"), weights.synthetic_weights())
@@ -76,9 +78,15 @@ def main():
     from svision_b200 import predict
     t = time.perf_counter()                                # -m loader (TF bundle, no TF) + weight repack + workspaces
     clf = predict.get_classifier(os.path.join(out, "model.ckpt"), device=int(os.environ.get("LOCAL_RANK", rank)))
-    clf.classify(sites.make_sites_p1(4096))               # first-launch warm-up
+    # warm start: first launches, and the GPU out of its idle power state (a rank that had waited a few
+    # seconds at the barrier measured 0.57 s for its first 65 k-row chunk against 0.19 s warm; a
+    # whole-genome run pays that once)
+    warm = sites.make_sites_p1(65536)
+    clf.classify(warm)
     t_model = time.perf_counter() - t
-    if world > 1:
+    if world > 1:                                         # ranks finish their preparations at different times:
+        dist.barrier()                                    # meet, warm again (an idle GPU has clocked down), meet
+        clf.classify(warm)
         dist.barrier()
     t = time.perf_counter()
     rc = step2.main(argv, classifier=clf, genotype_for=aligns.get if (rank == 0 or by_chrom) else None)
