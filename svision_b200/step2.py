@@ -132,40 +132,75 @@ def score_range(predict_dir: str) -> Tuple[np.float64, np.float64]:
     return np.max(scores), np.min(scores)
 
 
+def chromosome_summary(predict_dir: str, chrom: str, min_support) -> Tuple[int, int, Optional[float], Optional[float]]:
+    """(records, distinct (POS, END) runs, max score, min score) of one chromosome's result files: what
+    the merge needs to know about a chromosome before it can number and rescale the ones after it."""
+    prefix = predict_paths(predict_dir, chrom, min_support)
+    n = runs = 0
+    prev = None
+    with open(prefix + ".vcf") as f:
+        for record in f:
+            cols = record.split("\t", 8)
+            key = (cols[1], cols[7].split(";", 1)[0][4:])
+            if key != prev:
+                prev = key
+                runs += 1
+            n += 1
+    hi = lo = None
+    with open(prefix + ".score.txt") as f:
+        for line in f:
+            t = line.strip()
+            if t == "0":
+                continue
+            v = float(t)
+            hi = v if hi is None or v > hi else hi
+            lo = v if lo is None or v < lo else lo
+    return n, runs, hi, lo
+
+
+def merge_chromosome_records(predict_dir: str, chrom: str, min_support, serial: int, max_score, min_score,
+                             out) -> Tuple[int, int]:
+    """One chromosome's records with final IDs and rescaled QUAL written to ``out`` (output.py:307-345).
+    ``serial`` is the ID of the last record written before this chromosome (-1 at the start); returns
+    (the ID of this chromosome's last run, records written).  IDs count records whose (POS, END) differ from the previous
+    record's; a record repeating the previous (POS, END) becomes ``<id>_<k>`` (output.py:318-331); the
+    comparison starts afresh in every chromosome.  QUAL becomes
+    ``int(100 - round((q - min) / (max - min), 2) * 100)``, or 100 when all scores are equal
+    (output.py:334-341)."""
+    span = max_score - min_score
+    prev_key, sub, n = None, 1, 0
+    with open(predict_paths(predict_dir, chrom, min_support) + ".vcf") as f:
+        for record in f:
+            cols = record.split("\t", 8)
+            key = (cols[1], cols[7].split(";", 1)[0][4:])              # POS, END=<..>
+            if key == prev_key:
+                cols[2] = f"{serial}_{sub}"
+                sub += 1
+            else:
+                prev_key, sub = key, 1
+                serial += 1
+                cols[2] = str(serial)
+            q = 100
+            if max_score != min_score:
+                q = int(100 - (round((float(cols[5]) - min_score) / span, 2) * 100))
+            cols[5] = str(q)
+            out.write("\t".join(cols))
+            n += 1
+    return serial, n
+
+
 def merge_chromosomes(predict_dir: str, merged_vcf_path: str, max_score, min_score, chroms: Sequence[str],
                       options, contigs: Optional[Iterable[Tuple[str, int]]] = None) -> int:
     """Header + every chromosome's records with final IDs and rescaled QUAL (output.py:251-348).
-
-    IDs count records whose (POS, END) differ from the previous record's, from 0; a record repeating
-    the previous (POS, END) becomes ``<id>_<k>`` (output.py:318-331).  QUAL becomes
-    ``int(100 - round((q - min) / (max - min), 2) * 100)``, or 100 when all scores are equal
-    (output.py:334-341).  Returns the number of records written."""
+    Returns the number of records written."""
     if contigs is None:
         contigs = contigs_from_fai(options.genome)
-    span = max_score - min_score
-    n = 0
     with open(merged_vcf_path, "w") as out:
         out.write("\n".join(header_lines(contigs, options.sample, bool(getattr(options, "graph", False)))) + "\n")
-        serial = -1
+        serial, n = -1, 0
         for chrom in chroms:
-            prev_key, sub = None, 1
-            with open(predict_paths(predict_dir, chrom, options.min_support) + ".vcf") as f:
-                for record in f:
-                    cols = record.split("\t")
-                    key = (cols[1], cols[7].split(";")[0][4:])              # POS, END=<..>
-                    if key == prev_key:
-                        cols[2] = f"{serial}_{sub}"
-                        sub += 1
-                    else:
-                        prev_key, sub = key, 1
-                        serial += 1
-                        cols[2] = str(serial)
-                    q = 100
-                    if max_score != min_score:
-                        q = int(100 - (round((float(cols[5]) - min_score) / span, 2) * 100))
-                    cols[5] = str(q)
-                    out.write("\t".join(cols))
-                    n += 1
+            serial, k = merge_chromosome_records(predict_dir, chrom, options.min_support, serial, max_score, min_score, out)
+            n += k
     return n
 
 
@@ -297,14 +332,36 @@ def main(argv=None, classifier=None, genotype_for: Optional[Callable] = None) ->
             mine = assign_chromosomes(chroms, segments_dir, world)[rank]
             done = predict_chromosomes(mine, segments_dir, predict_dir, options, classifier, genotype_for)
             t1 = time.perf_counter()
+            # the merge in parallel too: IDs run on through the chromosomes and QUAL needs the global score
+            # range, so the ranks first exchange (records, ID runs, max, min) per chromosome, then every rank
+            # writes the final text of its own chromosomes and rank 0 only concatenates
+            mine_done = [c for c in mine if c in done]
+            summary = {c: chromosome_summary(predict_dir, c, options.min_support) for c in mine_done}
             everyone = [None] * world
-            dist.all_gather_object(everyone, sorted(done))               # also the barrier: all files are written
+            dist.all_gather_object(everyone, summary)                    # also the barrier: all files are written
             t2 = time.perf_counter()
+            info = {c: v for part in everyone for c, v in part.items()}
+            order = [c for c in chroms if c in info]
+            his = [v[2] for v in info.values() if v[2] is not None]
+            if not his:
+                raise ValueError("no scores under " + predict_dir + ": nothing was called")
+            hi, lo = np.max(his), np.min([v[3] for v in info.values() if v[3] is not None])
+            serial = -1
+            for c in order:
+                if c in summary:
+                    with open(predict_paths(predict_dir, c, options.min_support) + ".final.vcf", "w") as out:
+                        merge_chromosome_records(predict_dir, c, options.min_support, serial, hi, lo, out)
+                serial += info[c][1]
+            dist.barrier()
             merged = os.path.join(options.out_path, f"{options.sample}.svision.s{options.min_support}.vcf")
             if rank == 0:
-                have = {c for part in everyone for c in part}
-                hi, lo = score_range(predict_dir)
-                merge_chromosomes(predict_dir, merged, hi, lo, [c for c in chroms if c in have], options, contigs)
+                with open(merged, "wb") as out:
+                    out.write(("\n".join(header_lines(contigs, options.sample, bool(getattr(options, "graph", False)))) + "\n").encode())
+                    for c in order:
+                        part = predict_paths(predict_dir, c, options.min_support) + ".final.vcf"
+                        with open(part, "rb") as f:
+                            out.write(f.read())
+                        os.remove(part)
             t3 = time.perf_counter()
             dist.barrier()
             logging.info("rank %d: own chromosomes %s in %.3f s, waited %.3f s for the others, merge %.3f s",
