@@ -685,6 +685,11 @@ int launch_layer(const GemmLayer& L, int num_sms, cudaStream_t stream) {
         if ((L.m_rows / L.pos_per_img + 1) * (long long)(L.pool_h * L.pool_w) >= (1LL << 30))
             return fail(-1, "layer_tc: too many pooled rows for the epilogue's 30-bit row index");
         if (2 * L.grid_w + 3 >= BLOCK_M) return fail(-1, "layer_tc: pooling window spans more than one chunk boundary");
+        // windows per 128-row chunk: those that start in it (every other grid row, pool_w each) plus those
+        // cut by its upper boundary (started within the 2 * grid_w + 2 positions before it)
+        const int own = ((BLOCK_M / L.grid_w) / 2 + 2) * L.pool_w;
+        const int cut = (((2 * L.grid_w + 2) / L.grid_w) / 2 + 1) * L.pool_w;
+        if (own + cut > POOL_MAX_WINDOWS) return fail(-1, "layer_tc: too many pooling windows per chunk for the epilogue's list");
     }
     switch (L.block_n) {
         case 96: return launch_passes<96>(L, num_sms, stream);

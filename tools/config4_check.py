@@ -10,7 +10,14 @@ the calls of all ranks meet in every rank's gathered buffer when the last micro-
 publishes its flag).  Rank 0 then compares ALL rows with the committed oracle calls
 (tests/golden/config4_oracle_calls.npz: labels equal except at near-ties of the oracle's own top-2
 logits, scores within 1e-3) and the VCF text of the GPU-fed pipeline with the oracle-fed one (same
-records, QUAL within +-2).  Prints one JSON line on rank 0."""
+records, QUAL within +-2).  Prints one JSON line on rank 0.
+
+``--profile ont [--rows 100000]`` is BASELINE configs[4] (ONT-profile long/noisy segments; --contig only
+changes what happens upstream of the path and sets min_support to 1): no oracle calls are committed for
+it, so the gathered result of all ranks is compared, bit for bit, with rank 0 classifying the whole stream
+alone, the 256 known-answer rows embedded in the stream are compared with their golden labels / softmax,
+and the VCF text (min_support 1) of the two must be identical."""
+import argparse
 import json
 import os
 import sys
@@ -30,6 +37,10 @@ NEAR_TIE = 2e-3
 
 
 def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--profile", default="hifi", choices=["hifi", "ont"])
+    ap.add_argument("--rows", type=int, default=100_000, help="ont only (hifi uses the committed stream)")
+    a = ap.parse_args()
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", rank))
     torch.cuda.set_device(local)
@@ -37,6 +48,8 @@ def main():
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
+    if a.profile == "ont":
+        return ont_check(a, rank, world, local, dev)
     g = np.load(os.path.join(ROOT, "tests", "golden", "config4_oracle_calls.npz"))
     n, seed = (int(v) for v in g["meta"])
     table = sites.make_region_table(n, seed=seed, profile="hifi")            # every rank: same seeded stream
@@ -100,6 +113,67 @@ def main():
                "vcf_records": len(got), "vcf_records_identical_except_qual": bool(same_records),
                "max_abs_qual_diff": worst, "host_calls_s": round(time.perf_counter() - t, 2), "parity_ok": bool(ok)}
         print(json.dumps(out), flush=True)
+    clf.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0 if ok else 1
+
+
+def ont_check(a, rank, world, local, dev):
+    n = a.rows
+    table = sites.make_region_table(n, seed=sites.SEED_CONFIG5, profile="ont")
+    gold = np.load(os.path.join(ROOT, "tests", "golden", "cnn_golden.npz"))
+    rng = np.random.default_rng(sites.SEED_CONFIG5)
+    where = np.sort(rng.choice(n, size=256, replace=False))
+    rows = table.rows.copy()
+    rows[where] = gold["rows"][:256]
+    clf = C.Classifier(weights.synthetic_weights(), device=local, max_batch=10_000)
+    mine = clf.rows_to_device(sharded.shard_rows(rows, world, rank))
+    per = mine.shape[0]
+    x = sharded.Exchange(clf, per)
+    x.classify(mine)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    iters = 5
+    e0.record()
+    for _ in range(iters):
+        labels_d, scores_d = x.classify(mine)
+    e1.record()
+    torch.cuda.synchronize()
+    x.status()
+    ms = torch.tensor([e0.elapsed_time(e1) / iters], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    labels = labels_d[:n].cpu().numpy().astype(np.int32)
+    scores = scores_d[:n].cpu().numpy()
+    x.close()
+    ok = True
+    if rank == 0:
+        l1, s1 = clf.classify_device_calls(clf.rows_to_device(rows))         # the whole stream on one GPU
+        l1, s1 = l1.cpu().numpy(), s1.cpu().numpy()
+        bits = bool(np.array_equal(l1, labels) and np.array_equal(s1, scores))
+        logits = gold["logits_fp64"][:256]
+        e = np.exp(logits - logits.max(1, keepdims=True))
+        p = e / e.sum(1, keepdims=True)
+        kl = logits.argmax(1).astype(np.int32)
+        known = bool(np.array_equal(labels[where], kl)) and float(np.abs(scores[where] - p[np.arange(256), kl]).max()) < 1e-3
+        aln = sites.make_alignments(table, seed=2)
+        at = calls.AlignmentTable(aln["contig_length"], aln["reference_start"], aln["reference_end"],
+                                  aln["mapping_quality"], aln["is_unmapped"], aln["is_secondary"], aln["query_name"])
+        opt = types.SimpleNamespace(min_support=1, qname=True, min_sv_size=50, min_mapq=0, min_gt_depth=4,
+                                    homo_thresh=0.8, hete_thresh=0.2, bam_path="synthetic.bam")   # --contig: SVision:161-162
+        def vcf(l, s):
+            pr = np.zeros((n, 5), np.float32)
+            pr[np.arange(n), l] = s
+            return [line for _, line in calls.call_chromosome(table, l, pr, opt, at)]
+        va, vb = vcf(labels, scores), vcf(l1, s1)
+        ok = bits and known and va == vb
+        print(json.dumps({"world": world, "profile": "ont", "contig_mode": True, "rows": n, "sites_per_rank": per,
+                          "classify_ms": float(ms.item()), "sites_per_s": n / float(ms.item()) * 1e3,
+                          "gathered_equals_single_gpu_bits": bits, "known_answers_ok": known,
+                          "vcf_records": len(va), "vcf_identical": va == vb, "parity_ok": bool(ok)}), flush=True)
     clf.close()
     if world > 1:
         dist.destroy_process_group()

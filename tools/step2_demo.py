@@ -32,6 +32,9 @@ def main():
     ap.add_argument("--chroms", type=int, default=3)
     ap.add_argument("--out", default=None)
     ap.add_argument("--shard", default="auto", choices=["auto", "chrom", "rows"])
+    ap.add_argument("--profile", default="hifi", choices=["hifi", "ont"],
+                    help="segment-length profile of the synthetic rows (SURVEY 8(d): ont = BASELINE configs[4])")
+    ap.add_argument("--contig", action="store_true", help="pass the reference's --contig flag (min_support 1)")
     a = ap.parse_args()
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
     out = a.out or os.path.join(tempfile.gettempdir(), "svx_step2_demo")
@@ -43,7 +46,8 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl")
     def table_of(k):
-        return sites.make_region_table(a.rows, seed=sites.SEED_CONFIG4 + 10 * k, contig=names[k])
+        seed = (sites.SEED_CONFIG4 if a.profile == "hifi" else sites.SEED_CONFIG5) + 10 * k
+        return sites.make_region_table(a.rows, seed=seed, profile=a.profile, contig=names[k])
 
     # every rank prepares the segment files of chromosomes k = rank (mod world): Step 1's output
     tables = {}
@@ -74,7 +78,7 @@ def main():
                                              al["query_name"])
 
     argv = ["-o", out, "-b", "synthetic.bam", "-m", os.path.join(out, "model.ckpt"), "-g", os.path.join(out, "genome.fa"),
-            "-n", "demo", "-s", "3", "--debug", "--shard", a.shard]
+            "-n", "demo", "-s", "3", "--debug", "--shard", a.shard] + (["--contig"] if a.contig else [])
     from svision_b200 import predict
     t = time.perf_counter()                                # -m loader (TF bundle, no TF) + weight repack + workspaces
     clf = predict.get_classifier(os.path.join(out, "model.ckpt"), device=int(os.environ.get("LOCAL_RANK", rank)))
@@ -92,10 +96,10 @@ def main():
     rc = step2.main(argv, classifier=clf, genotype_for=aligns.get if (rank == 0 or by_chrom) else None)
     dt = time.perf_counter() - t
     if rank == 0:
-        merged = os.path.join(out, "demo.svision.s3.vcf")
+        merged = os.path.join(out, "demo.svision.s1.vcf" if a.contig else "demo.svision.s3.vcf")
         text = open(merged, "rb").read()
         print(json.dumps({"world": world, "rc": rc, "shard": "chrom" if by_chrom else ("rows" if world > 1 else "none"),
-                          "chromosomes": a.chroms, "rows": a.rows * a.chroms,
+                          "profile": a.profile, "contig_mode": a.contig, "chromosomes": a.chroms, "rows": a.rows * a.chroms,
                           "model_load_s": round(t_model, 3), "step2_s": round(dt, 3), "rows_per_s": round(a.rows * a.chroms / dt),
                           "records": sum(1 for l in text.split(b"\n") if l and not l.startswith(b"#")),
                           "merged_sha256": hashlib.sha256(text).hexdigest()}), flush=True)
