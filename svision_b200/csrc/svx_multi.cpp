@@ -167,15 +167,11 @@ int svx_multi_classify(svx_multi* m, const int32_t* rows_host, int64_t n, int32_
     const int ndev = (int)m->devices.size();
     for (int i = 0; i < ndev; ++i) m->sites_done[i] = 0;
     if (n == 0) return SVX_OK;
-    // Chunks: an equal split when it fits one micro-batch per device; for long streams about four
-    // chunks per device (never below 2048 sites, where the fc layers' tile waves get ragged), so that
-    // the shared counter can even out devices of different speed
-    int64_t chunk = (n + ndev - 1) / ndev;
-    if (chunk > m->max_batch) {
-        chunk = (n + 4 * ndev - 1) / (4 * ndev);
-        if (chunk < 2048) chunk = 2048;
-        if (chunk > m->max_batch) chunk = m->max_batch;
-    }
+    // Chunks: k equal chunks per device, k the fewest that fit the micro-batch (an equal split, one
+    // pass each, when the call fits).  With devices of equal speed every device takes k chunks; a slower
+    // one takes fewer, because the chunks are handed out through a shared counter.
+    const int64_t rounds = (n + (int64_t)ndev * m->max_batch - 1) / ((int64_t)ndev * m->max_batch);
+    const int64_t chunk = (n + ndev * rounds - 1) / (ndev * rounds);
     {
         std::lock_guard<std::mutex> lock(m->mu);
         m->rows = rows_host;
