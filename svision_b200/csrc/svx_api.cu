@@ -144,15 +144,37 @@ struct svx_exchange {
 
 namespace {
 
+// Is the primary context of `dev` alive in this process?  (driver entry point, resolved once)
+bool primary_context_active(int dev) {
+    typedef CUresult (*PFN_state)(CUdevice, unsigned int*, int*);
+    static PFN_state fn = [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuDevicePrimaryCtxGetState", &p, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess)
+            p = nullptr;
+        return reinterpret_cast<PFN_state>(p);
+    }();
+    if (!fn) return true;                       // cannot tell: behave as before
+    unsigned int flags = 0;
+    int active = 0;
+    return fn((CUdevice)dev, &flags, &active) == CUDA_SUCCESS ? active != 0 : true;
+}
+
+// Makes the handle's device current for the duration of a call and gives the caller's device back
+// afterwards -- unless that would CREATE a context there: since CUDA 12 cudaSetDevice initialises the
+// device's primary context, and a thread that never touched CUDA has device 0 as its "current" one.
+// Restoring it blindly made every process that drives GPU 1..7 from a helper thread build a context on
+// GPU 0 (measured: 1.85 s on the first call of the thread, and ~0.5 GB of GPU 0's memory per process).
 struct DeviceGuard {
-    int prev = -1;
+    int prev = -1, cur = -1;
     bool ok = true;
-    explicit DeviceGuard(int dev) {
+    explicit DeviceGuard(int dev) : cur(dev) {
         if (cudaGetDevice(&prev) != cudaSuccess) ok = false;
         if (ok && prev != dev && cudaSetDevice(dev) != cudaSuccess) ok = false;
     }
     ~DeviceGuard() {
-        if (prev >= 0) cudaSetDevice(prev);
+        if (prev >= 0 && prev != cur && primary_context_active(prev)) cudaSetDevice(prev);
     }
 };
 
