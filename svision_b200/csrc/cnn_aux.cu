@@ -80,13 +80,8 @@ __global__ void __launch_bounds__(256) pool_kernel(const PoolParams p, long long
             for (int j = 0; j < CPL; ++j) out[j] = m[j];
         }
         if (active) {
-            long long o;
-            if (p.flatten) {
-                o = img * (long long)p.out_ld + (long long)(y * p.out_w + x) * p.C + c0;
-            } else {
-                o = (long long)(c0 / p.group_real) * p.group_elems +
-                    (img * p.out_pos_per_img + (long long)y * p.out_grid_w + x) * p.out_ld + (c0 % p.group_real);
-            }
+            const long long o = (long long)(c0 / p.group_real) * p.group_elems +
+                                (img * p.out_pos_per_img + (long long)y * p.out_grid_w + x) * p.out_ld + (c0 % p.group_real);
             uint32_t ph[CPL / 2], pl[CPL / 2];
 #pragma unroll
             for (int j = 0; j < CPL / 2; ++j) {
@@ -357,14 +352,15 @@ __global__ void split_hilo_kernel(const float* __restrict__ in, long long count,
 int launch_pool(const PoolParams& p, long long n_img, int num_sms, cudaStream_t stream) {
     const long long total = n_img * p.out_h * p.out_w;
     if (total <= 0) return 0;
-    const int cpl = p.C <= 128 ? 4 : 8;
+    // the one user left is the dense path's pool1 (96 channels: 24 lanes x 4); pool2 / pool5 run in the
+    // conv epilogues (layer_tc.cu) and are finished by finish_pooled_kernel
+    constexpr int cpl = 4;
     if (p.C % cpl != 0 || p.C / cpl > 32 || p.group_real % cpl != 0 || p.group_elems % cpl != 0 ||
         p.out_ld % cpl != 0)
         return fail(-1, "pool: unsupported channel count / grouping");
     long long blocks = (long long)num_sms * 8;           // 8 CTAs x 8 warps resident per SM
     if (blocks > (total + 7) / 8) blocks = (total + 7) / 8;
-    if (cpl == 4) pool_kernel<4><<<(unsigned)blocks, 256, 0, stream>>>(p, total);
-    else          pool_kernel<8><<<(unsigned)blocks, 256, 0, stream>>>(p, total);
+    pool_kernel<4><<<(unsigned)blocks, 256, 0, stream>>>(p, total);
     SVX_LAUNCH_CHECK("pool_kernel");
     return 0;
 }

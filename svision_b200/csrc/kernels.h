@@ -110,7 +110,6 @@ struct PoolParams {
     int group_real;            // channels per output group
     long long group_elems;     // element offset between groups: channel c of row r lives at
                                //   (c / group_real) * group_elems + r * out_ld + c % group_real
-    int flatten;               // 1: output is [n][out_h*out_w*C] (NHWC flatten for fc6)
 };
 int launch_pool(const PoolParams& p, long long n_img, int num_sms, cudaStream_t stream);
 

@@ -510,7 +510,7 @@ int dense_front(svx_handle* h, const void* images, int dtype, long long m, cudaS
     PoolParams p1{};
     p1.in = h->y1; p1.in_grid_w = S2D; p1.in_pos_per_img = P1; p1.C = 96; p1.out_h = 27; p1.out_w = 27;
     p1.lrn = 1; p1.out_hi = h->x2_hi; p1.out_lo = h->x2_lo; p1.out_ld = h->x2_ld; p1.out_grid_w = G2;
-    p1.out_pos_per_img = P2; p1.group_real = 48; p1.group_elems = h->x2_group_elems; p1.flatten = 0;
+    p1.out_pos_per_img = P2; p1.group_real = 48; p1.group_elems = h->x2_group_elems;
     mark(h, 2, st);
     return launch_pool(p1, m, h->num_sms, st);
 }
