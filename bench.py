@@ -312,12 +312,12 @@ def run_reference(args):
     w = weights.synthetic_weights()
     rows_all = sites.make_sites_p1(SITES_PER_GPU, seed=sites.SEED_CONFIG2)
     ref = CpuReference(w)
-    # step size: the whole 10 000-site workload when the run then still ends within ~4 minutes,
+    # step size: the whole 10 000-site workload when the run then still ends within ~5 minutes,
     # otherwise a bounded sample of it (the rate does not depend on the sample: sites are independent
     # and every image costs the same dense CNN)
     rate0, _ = ref.run(rows_all[:1024])
     steps_total = args.steps + args.warmup
-    sample = int(os.environ.get("SVX_REF_SAMPLE", 0)) or int(min(SITES_PER_GPU, max(1024, rate0 * 220 / steps_total)))
+    sample = int(os.environ.get("SVX_REF_SAMPLE", 0)) or int(min(SITES_PER_GPU, max(1024, rate0 * 300 / steps_total)))
     sample = min(SITES_PER_GPU, -(-sample // 128) * 128) if sample < SITES_PER_GPU else SITES_PER_GPU
     for i in range(args.warmup):
         ref.run(rows_all[:sample])
