@@ -127,7 +127,8 @@ int svx_classify_device_calls(svx_handle *h, const int32_t *rows_dev, int64_t n,
  * preserved, no gather).  Same results as svx_classify, bit for bit: sites are independent.
  *   devices[ndev]   CUDA device ordinals, distinct
  *   max_batch       micro-batch per device (as svx_create)
- * svx_multi_last_split reports how many sites each device processed in the last call. */
+ * svx_multi_last_split reports how many sites each device processed in the last call.  Like a single
+ * handle, an svx_multi is externally synchronised: one svx_multi_classify at a time. */
 typedef struct svx_multi svx_multi;
 int svx_multi_create(const svx_weights *weights, const int *devices, int ndev, int64_t max_batch,
                      int precision, svx_multi **out);
