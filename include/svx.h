@@ -185,6 +185,10 @@ int svx_conv_selftest(int device, const float *a_dev, const float *b_dev, float 
                       int64_t n, int64_t k_per_tap, int taps, const int *row_off, int block_n,
                       int precision, void *stream);
 
+/* Milliseconds the layer kernel of the calling thread's last svx_gemm_selftest / svx_conv_selftest took
+ * (CUDA events on its stream; the operand conversion around it is not included). */
+float svx_selftest_last_ms(void);
+
 /* Development aid: per-role cycle counters of the 7 tensor-core layers, uint64 out[7][8]
  * (handle created with SVX_DBG=1 in the environment -- besides SVX_EXCHANGE_TIMEOUT_MS the only
  * environment variable the library reads): 0 MMA-role total, 1 MMA wait operands,

@@ -22,7 +22,7 @@ SYMBOLS = (
     "svx_classify_exchange", "svx_exchange_status", "svx_exchange_destroy",
     "svx_calls_aggregate", "svx_np_mean_f32", "svx_np_std_i64",
     "svx_multi_create", "svx_multi_classify", "svx_multi_device_count", "svx_multi_last_split",
-    "svx_multi_destroy",
+    "svx_multi_destroy", "svx_selftest_last_ms",
 )
 IPC_HANDLE_BYTES = 72
 
@@ -115,6 +115,8 @@ def load() -> ctypes.CDLL:
     lib.svx_multi_last_split.restype = i32
     lib.svx_multi_destroy.argtypes = [vp]
     lib.svx_multi_destroy.restype = None
+    lib.svx_selftest_last_ms.argtypes = []
+    lib.svx_selftest_last_ms.restype = ctypes.c_float
     lib.svx_max_batch.argtypes = [vp]
     lib.svx_max_batch.restype = i64
     lib.svx_device.argtypes = [vp]

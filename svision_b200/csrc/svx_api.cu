@@ -905,6 +905,8 @@ int svx_debug_activation(svx_handle* h, const char* name, int64_t n, float* out_
     return fail(SVX_ERR_INVALID, std::string("svx_debug_activation: unknown activation '") + name + "'");
 }
 
+static thread_local float g_selftest_ms = 0.f;
+
 // Shared by the two self-test entries: fp32 operands on the device -> hi/lo planes -> one launch of
 // the layer kernel with `taps` row offsets -> fp32 result.
 static int layer_selftest(int device, const float* a_dev, const float* b_dev, float* c_dev, int64_t m,
@@ -944,9 +946,20 @@ static int layer_selftest(int device, const float* a_dev, const float* b_dev, fl
     if ((rc = make_tensor_map_2d(&L.tm_a_lo, a_lo, m, k_per_tap, k_per_tap, L.slab_rows))) return free_all(rc);
     if ((rc = make_tensor_map_2d(&L.tm_b_hi, b_hi, n, k, k, block_n / 2))) return free_all(rc);
     if ((rc = make_tensor_map_2d(&L.tm_b_lo, b_lo, n, k, k, block_n / 2))) return free_all(rc);
+    // the layer kernel alone, timed on its stream (svx_selftest_last_ms)
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    cudaEventRecord(e0, st);
     rc = launch_layer(L, prop.multiProcessorCount, st);
+    cudaEventRecord(e1, st);
+    if (rc == 0 && cudaEventSynchronize(e1) == cudaSuccess) cudaEventElapsedTime(&g_selftest_ms, e0, e1);
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
     return free_all(rc);
 }
+
+float svx_selftest_last_ms(void) { return g_selftest_ms; }
 
 int svx_gemm_selftest(int device, const float* a_dev, const float* b_dev, float* c_dev, int64_t m,
                       int64_t n, int64_t k, int block_n, int precision, void* stream) {
