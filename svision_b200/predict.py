@@ -112,7 +112,7 @@ def run_predict(segments_out_file: str, out_path_prefix: str, options, aggregate
         # classification of the next chunk of regions overlaps the record assembly of this one
         t0 = time.perf_counter()
         records = calls.call_chromosome_streamed(table, clf.classify, options, genotype,
-                                                 chunk_rows=getattr(options, "chunk_rows", 65536))
+                                                 chunk_rows=getattr(options, "chunk_rows", 16384))
         t_calls = time.perf_counter() - t0
         calls.write_chromosome(out_path_prefix, records)
         logging.info("%s: %d rows: parse %.3f s, classify + calls %.3f s, write %.3f s -> %d records",
