@@ -105,7 +105,14 @@ __device__ __forceinline__ void conv1_at(const uint32_t* bm, const FrontParams& 
     }
 }
 
-__global__ void __launch_bounds__(FRONT_THREADS, 4)
+#ifndef SVX_FRONT_CTAS
+#define SVX_FRONT_CTAS 4          // resident CTAs per SM the register budget is set for
+#endif
+#ifndef SVX_FRONT_CARVE
+#define SVX_FRONT_CARVE 72        // shared-memory carve-out in percent (the rest is L1 for the conv1 weights)
+#endif
+
+__global__ void __launch_bounds__(FRONT_THREADS, SVX_FRONT_CTAS)
 front_kernel(const int32_t* __restrict__ rows, long long n, const FrontParams P) {
     __shared__ __align__(16) uint32_t bm[3 * PLANE];
     __shared__ LineParams lines[2];
@@ -345,7 +352,7 @@ int launch_front(const int32_t* rows_dev, long long n, const FrontParams& P, int
         // 4 CTAs x 38 KB of shared memory fit the 164 KB configuration, which leaves ~90 KB of L1 for
         // the conv1 weight vectors phase A walks (the channel-0 vectors alone are 46 KB); with the
         // maximum carve-out L1 was ~25 KB and half of those loads went to L2
-        cudaFuncSetAttribute(front_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 72);
+        cudaFuncSetAttribute(front_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, SVX_FRONT_CARVE);
         int nb = 0;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, front_kernel, bitmap::FRONT_THREADS, 0) !=
                 cudaSuccess || nb < 1)
