@@ -315,7 +315,8 @@ def run_reference(args):
     # step size: the whole 10 000-site workload when the run then still ends within ~5 minutes,
     # otherwise a bounded sample of it (the rate does not depend on the sample: sites are independent
     # and every image costs the same dense CNN)
-    rate0, _ = ref.run(rows_all[:1024])
+    ref.run(rows_all[:1024])                             # cold: worker start-up, first-touch of the weights
+    rate0, _ = ref.run(rows_all[:2048])
     steps_total = args.steps + args.warmup
     sample = int(os.environ.get("SVX_REF_SAMPLE", 0)) or int(min(SITES_PER_GPU, max(1024, rate0 * 300 / steps_total)))
     sample = min(SITES_PER_GPU, -(-sample // 128) * 128) if sample < SITES_PER_GPU else SITES_PER_GPU
