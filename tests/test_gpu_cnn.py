@@ -222,3 +222,15 @@ def test_gpu_matches_the_independent_numpy_oracle(clf, synthetic_weights):
     for name in ("norm1", "norm2", "pool5", "fc7"):
         got, ref = clf.debug_activation(name, rows.shape[0]), inter[name]
         assert np.abs(got - ref).max() < 2e-4 * np.abs(ref).max() + 1e-5, name
+
+
+@pytest.mark.parametrize("max_batch", [1, 3, 129])
+def test_odd_micro_batches_match_oracle(max_batch, cnn_golden, synthetic_weights):
+    """Micro-batches far from any tile size (one image = 841 conv2 rows = 3.3 pair tiles; fewer tiles than
+    CTA pairs; pooling windows of the last image cut by the last chunk): same answers."""
+    rows = cnn_golden["rows"][:37]
+    ref_logits = torch.from_numpy(cnn_golden["logits_fp64"][:37])
+    with C.Classifier(synthetic_weights, device=0, max_batch=max_batch) as c:
+        labels, probs = c.classify(rows)
+    assert np.array_equal(labels, ref_logits.argmax(1).numpy().astype(np.int32))
+    assert np.abs(probs - torch.softmax(ref_logits, 1).numpy()).max() < SOFTMAX_TOL
