@@ -69,7 +69,7 @@ def stage_cnn():
         rd = clf.rows_to_device(rows)
         labels, probs, logits = clf.classify_device(rd, want_logits=True)
         torch.cuda.synchronize()
-        for name in ("norm1", "conv2", "norm2", "conv3", "conv4", "conv5", "pool5", "fc6", "fc7"):
+        for name in ("norm1", "norm2", "conv3", "conv4", "pool5", "fc6", "fc7"):   # conv2 / conv5 are never materialised
             got = clf.debug_activation(name, rows.shape[0])
             ref = inter[name].numpy()
             err = np.abs(got - ref).max()
