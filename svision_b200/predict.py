@@ -29,12 +29,18 @@ from . import bed as _bed
 _CLASSIFIER_CACHE = {}
 
 
-def get_classifier(model_path, device: int = 0, max_batch: int = 8192):
-    """Process-wide classifier for ``-m model_path`` (amortises the checkpoint load)."""
-    from .classifier import Classifier
-    key = (str(model_path), int(device))
+def get_classifier(model_path, device: int = 0, max_batch: int = 8192, devices=None):
+    """Process-wide classifier for ``-m model_path`` (amortises the checkpoint load).  ``devices`` with
+    more than one entry gives ONE object driving all of them from this process (``MultiClassifier``,
+    C-ABI ``svx_multi_*``): the reference's single-process model (``SVision:296-341``) on a multi-GPU box."""
+    from .classifier import Classifier, MultiClassifier
+    devs = tuple(int(d) for d in devices) if devices is not None else (int(device),)
+    key = (str(model_path), devs)
     if key not in _CLASSIFIER_CACHE:
-        _CLASSIFIER_CACHE[key] = Classifier(model_path, device=device, max_batch=max_batch)
+        if len(devs) > 1:
+            _CLASSIFIER_CACHE[key] = MultiClassifier(model_path, devices=list(devs), max_batch=max_batch)
+        else:
+            _CLASSIFIER_CACHE[key] = Classifier(model_path, device=devs[0], max_batch=max_batch)
     return _CLASSIFIER_CACHE[key]
 
 

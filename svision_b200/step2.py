@@ -255,6 +255,9 @@ def parse_arguments(argv=None):
     pred.add_argument("--homo_thresh", type=float, default=0.8)
     pred.add_argument("--hete_thresh", type=float, default=0.2)
     pred.add_argument("--device", type=int, default=0, help="CUDA device (not a reference flag)")
+    pred.add_argument("--devices", type=str, default=None,
+                      help="'all' or a comma-separated list: ONE process drives these GPUs through svx_multi_* "
+                           "(the reference's single-process model; without torchrun; not a reference flag)")
     pred.add_argument("--shard", choices=("auto", "chrom", "rows"), default="auto",
                       help="under torchrun: whole chromosomes per rank (each rank parses, classifies, aggregates "
                            "and genotypes its own; rank 0 merges) or the rows of every chunk over the ranks; auto = "
@@ -324,7 +327,12 @@ def main(argv=None, classifier=None, genotype_for: Optional[Callable] = None) ->
             if genotype_for is None:
                 genotype_for = lambda chrom: (lambda *a: ("./.", 0, 0))    # noqa: E731
     if classifier is None:
-        classifier = _predict.get_classifier(options.model_path, device=options.device)
+        devices = None
+        if options.devices and world == 1:
+            import torch
+            devices = list(range(torch.cuda.device_count())) if options.devices == "all" else \
+                [int(d) for d in options.devices.split(",") if d.strip()]
+        classifier = _predict.get_classifier(options.model_path, device=options.device, devices=devices)
     try:
         if by_chrom:
             import time

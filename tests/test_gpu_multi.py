@@ -86,3 +86,23 @@ def test_bench_two_gpus_checks_every_rank_slice():
     assert res["parity_spot_check"]["known_answers_checked"] == 2 * 256
     assert res["parity_spot_check"]["ok"] is True
     assert res["strong_100k"]["parity_ok"] is True
+
+
+def test_get_classifier_with_a_device_list(synthetic_weights, tmp_path, cnn_golden):
+    """predict.get_classifier(devices=[...]): one device -> a plain Classifier; two -> ONE object driving both
+    from this process (what `python -m svision_b200.step2 --devices all` uses), same bits."""
+    from svision_b200 import predict, tf_bundle
+    prefix = str(tmp_path / "m.ckpt")
+    tf_bundle.write_bundle(prefix, synthetic_weights, data_crc=False)
+    one = predict.get_classifier(prefix, devices=[0], max_batch=256)
+    assert isinstance(one, C.Classifier)
+    rows = cnn_golden["rows"]
+    l1, p1 = one.classify(rows)
+    if torch.cuda.device_count() >= 2:
+        two = predict.get_classifier(prefix, devices=[0, 1], max_batch=256)
+        assert isinstance(two, C.MultiClassifier)
+        l2, p2 = two.classify(rows)
+        assert np.array_equal(l1, l2) and np.array_equal(p1, p2) and min(two.last_split()) > 0
+        two.close()
+    one.close()
+    predict._CLASSIFIER_CACHE.clear()

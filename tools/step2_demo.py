@@ -35,6 +35,8 @@ def main():
     ap.add_argument("--profile", default="hifi", choices=["hifi", "ont"],
                     help="segment-length profile of the synthetic rows (SURVEY 8(d): ont = BASELINE configs[4])")
     ap.add_argument("--contig", action="store_true", help="pass the reference's --contig flag (min_support 1)")
+    ap.add_argument("--devices", default=None,
+                    help="without torchrun: 'all' or '0,1,...' -- this ONE process drives these GPUs through svx_multi_*")
     a = ap.parse_args()
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
     out = a.out or os.path.join(tempfile.gettempdir(), "svx_step2_demo")
@@ -81,7 +83,12 @@ def main():
             "-n", "demo", "-s", "3", "--debug", "--shard", a.shard] + (["--contig"] if a.contig else [])
     from svision_b200 import predict
     t = time.perf_counter()                                # -m loader (TF bundle, no TF) + weight repack + workspaces
-    clf = predict.get_classifier(os.path.join(out, "model.ckpt"), device=int(os.environ.get("LOCAL_RANK", rank)))
+    devices = None
+    if a.devices and world == 1:
+        import torch
+        devices = list(range(torch.cuda.device_count())) if a.devices == "all" else [int(d) for d in a.devices.split(",")]
+    clf = predict.get_classifier(os.path.join(out, "model.ckpt"), device=int(os.environ.get("LOCAL_RANK", rank)),
+                                 devices=devices)
     # warm start: first launches, and the GPU out of its idle power state (a rank that had waited a few
     # seconds at the barrier measured 0.57 s for its first 65 k-row chunk against 0.19 s warm; a
     # whole-genome run pays that once)
@@ -99,6 +106,7 @@ def main():
         merged = os.path.join(out, "demo.svision.s1.vcf" if a.contig else "demo.svision.s3.vcf")
         text = open(merged, "rb").read()
         print(json.dumps({"world": world, "rc": rc, "shard": "chrom" if by_chrom else ("rows" if world > 1 else "none"),
+                          "devices_in_this_process": len(devices) if devices else 1,
                           "profile": a.profile, "contig_mode": a.contig, "chromosomes": a.chroms, "rows": a.rows * a.chroms,
                           "model_load_s": round(t_model, 3), "step2_s": round(dt, 3), "rows_per_s": round(a.rows * a.chroms / dt),
                           "records": sum(1 for l in text.split(b"\n") if l and not l.startswith(b"#")),
