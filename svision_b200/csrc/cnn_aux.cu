@@ -220,12 +220,32 @@ fc8_softmax_kernel(const __half* __restrict__ x_hi, const __half* __restrict__ x
         const __half* xh = x_hi + site * 4096;
         const __half* xl = x_lo + site * 4096;
         float acc[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
-        for (int i = 0; i < 128; ++i) {
-            const int k = lane + 32 * i;
-            const float x = __half2float(xh[k]) + __half2float(xl[k]);
-            const float* w = w8 + k * 5;
+        // 8 consecutive features per lane and pass: one 16-byte load per plane, the 40 weights of those
+        // features as ten 16-byte loads (w8 is [4096][5], so 8 rows are 160 contiguous bytes)
+        for (int i = 0; i < 16; ++i) {
+            const int k0 = 8 * lane + 256 * i;
+            const uint4 h = *reinterpret_cast<const uint4*>(xh + k0);
+            const uint4 l = *reinterpret_cast<const uint4*>(xl + k0);
+            const uint32_t hw[4] = {h.x, h.y, h.z, h.w}, lw[4] = {l.x, l.y, l.z, l.w};
+            float x[8];
 #pragma unroll
-            for (int j = 0; j < 5; ++j) acc[j] = fmaf(x, __ldg(w + j), acc[j]);
+            for (int q = 0; q < 4; ++q) {
+                x[2 * q] = __half2float(__ushort_as_half((unsigned short)(hw[q] & 0xFFFFu))) +
+                           __half2float(__ushort_as_half((unsigned short)(lw[q] & 0xFFFFu)));
+                x[2 * q + 1] = __half2float(__ushort_as_half((unsigned short)(hw[q] >> 16))) +
+                               __half2float(__ushort_as_half((unsigned short)(lw[q] >> 16)));
+            }
+            float w[40];
+            const float4* wp = reinterpret_cast<const float4*>(w8 + k0 * 5);
+#pragma unroll
+            for (int q = 0; q < 10; ++q) {
+                const float4 t = __ldg(wp + q);
+                w[4 * q] = t.x; w[4 * q + 1] = t.y; w[4 * q + 2] = t.z; w[4 * q + 3] = t.w;
+            }
+#pragma unroll
+            for (int e = 0; e < 8; ++e)
+#pragma unroll
+                for (int j = 0; j < 5; ++j) acc[j] = fmaf(x[e], w[5 * e + j], acc[j]);
         }
 #pragma unroll
         for (int j = 0; j < 5; ++j)
