@@ -439,13 +439,24 @@ def run_gpu(args):
             calls = gathered
         return calls[:, 0], calls[:, 1].view(torch.float32)
 
+    rows_stage = torch.empty_like(rows_dev)
+    calls_host = torch.empty((world * n, 2), dtype=torch.int32).pin_memory() if world > 1 else None
+
     def step_e2e():
-        clf.classify(rows_pinned.numpy(), labels_host.numpy(), probs_host.numpy())
-        if world > 1:
-            pair = torch.stack([labels_host, probs_host.gather(
-                1, labels_host.long().unsqueeze(1)).squeeze(1).view(torch.int32)], dim=1).to(dev, non_blocking=True)
-            dist.all_gather_into_tensor(gathered, pair)
-            torch.cuda.synchronize()
+        """End to end from pinned host rows to host results.  One GPU: the host entry svx_classify (labels +
+        probs back).  Several: this step's rows H2D, classify + exchange, and the gathered calls of ALL ranks
+        D2H on every rank (what each rank's downstream replay would read)."""
+        if world == 1:
+            clf.classify(rows_pinned.numpy(), labels_host.numpy(), probs_host.numpy())
+            return
+        rows_stage.copy_(rows_pinned, non_blocking=True)
+        if exchange is not None:
+            calls = exchange.classify(rows_stage, raw=True)
+        else:
+            dist.all_gather_into_tensor(gathered, clf.classify_device_calls(rows_stage, raw=True))
+            calls = gathered
+        calls_host.copy_(calls, non_blocking=True)
+        torch.cuda.synchronize()
 
     def barrier():
         if world > 1:
@@ -512,9 +523,12 @@ def run_gpu(args):
         exchange.status()
     l_all, s_all = l_step.cpu().numpy(), s_step.cpu().numpy()
     known_ok, known_err = check_known(l_all, s_all, world, n, k_labels, k_scores)
-    mine = slice(rank * n, (rank + 1) * n)
-    lh, ph = labels_host.numpy(), probs_host.numpy()
-    bits_ok = bool(np.array_equal(l_all[mine], lh)) and bool(np.array_equal(s_all[mine], ph[np.arange(n), lh]))
+    if world == 1:
+        lh, ph = labels_host.numpy(), probs_host.numpy()
+        bits_ok = bool(np.array_equal(l_all, lh)) and bool(np.array_equal(s_all, ph[np.arange(n), lh]))
+    else:                                                # what the e2e steps brought to the host == this step's
+        ch = calls_host.numpy()
+        bits_ok = bool(np.array_equal(l_all, ch[:, 0])) and bool(np.array_equal(s_all.view(np.int32), ch[:, 1]))
     parity_all = all_ranks({"known": known_ok, "err": known_err, "bits": bits_ok})
 
     # ---- configs[2]: 100 k HiFi sites strong-sharded, ONE exchange at the end of the stream --------
@@ -593,7 +607,7 @@ def run_gpu(args):
                              "fp16 hi/lo weights 226 MB both exceed the 126 MB L2; no flush needed"},
             "e2e": {"value": total_sites / e2e_s, "unit": UNIT,
                     "h2d_bytes_per_step": int(n * world * 48),
-                    "d2h_bytes_per_step": int(n * world * 24)},
+                    "d2h_bytes_per_step": int(n * 24) if world == 1 else int(world * world * n * 8)},
             "gpu_launches": int(launches),
             "clocks": clocks,
             # dominant kernel = the conv2 launch of the tensor-core layer kernel (largest single launch)
@@ -641,8 +655,8 @@ def run_gpu(args):
                 "ok": all(p["known"] and p["bits"] for p in parity_all),
                 "known_answers_checked": world * KNOWN,
                 "what": "every rank's slice of the gathered (label, score) buffer against the golden labels / "
-                        "softmax of tests/golden/cnn_golden.npz (checked on every rank); device entry == host "
-                        "entry bit for bit on each rank's own 10 000 sites",
+                        "softmax of tests/golden/cnn_golden.npz (checked on every rank); what the end-to-end "
+                        "steps brought to the host == the device-resident step, bit for bit",
                 "max_abs_score_err": max(p["err"] for p in parity_all),
                 "host_vs_device_bits": all(p["bits"] for p in parity_all)},
         }

@@ -143,10 +143,11 @@ class Exchange:
             self.close()
             raise err if err is not None else RuntimeError("exchange attach failed on another rank")
 
-    def classify(self, rows_dev: torch.Tensor):
+    def classify(self, rows_dev: torch.Tensor, raw: bool = False):
         """rows of this rank's shard (cuda int32 [n<=per,12]) -> (labels int32[world*per], scores
         float32[world*per]) in rank-major (= file) order: zero-copy views of the gathered buffer,
-        valid after the current stream's work and until the next-but-one call.  Asynchronous: a rank
+        valid after the current stream's work and until the next-but-one call (``raw=True``: the
+        buffer itself, int32[world*per, 2] with the score bit-cast in column 1).  Asynchronous: a rank
         that never delivers is detected by the wait kernel's timeout, see :meth:`status` /
         :meth:`result`."""
         clf = self.clf
@@ -156,6 +157,8 @@ class Exchange:
                                                     ctypes.byref(ptr), clf._stream()), "svx_classify_exchange")
         calls = torch.as_tensor(_DeviceView(ptr.value, (self.world * self.per, 2), "<i4"),
                                 device=clf.torch_device)
+        if raw:
+            return calls
         return calls[:, 0], calls[:, 1].view(torch.float32)
 
     def status(self) -> None:
